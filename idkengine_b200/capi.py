@@ -1,0 +1,177 @@
+"""ctypes declarations of include/idkpt.h -- the stand-in for the C# [LibraryImport] stubs of INTEGRATION.md.
+No compute lives here; this only marshals the engine's arrays across the C ABI."""
+import ctypes
+import os
+
+import numpy as np
+
+from . import build as _build
+
+c_i32, c_u32, c_u64, c_f = ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint64, ctypes.c_float
+c_vp = ctypes.c_void_p
+
+IDKPT_MAX_RAY_DEPTH = 64
+
+
+class IdkPtGpuSettings(ctypes.Structure):
+    _fields_ = [("FocalLength", c_f), ("LenseRadius", c_f), ("DoDebugBVHTraversal", c_i32),
+                ("DoTraceLights", c_i32), ("DoRussianRoulette", c_i32)]
+
+
+class IdkPtCreateInfo(ctypes.Structure):
+    _fields_ = [("Device", c_i32), ("Width", c_i32), ("Height", c_i32), ("TileStripeHeight", c_i32),
+                ("TileIndex", c_i32), ("TileCount", c_i32), ("Flags", c_u32)]
+
+
+class IdkPtSceneDesc(ctypes.Structure):
+    _fields_ = [
+        ("BlasNodes", c_vp), ("BlasNodeCount", c_u64),
+        ("BlasTriangles", c_vp), ("BlasTriangleCount", c_u64),
+        ("BlasDescs", c_vp), ("BlasDescCount", c_u64),
+        ("BlasInstances", c_vp), ("BlasInstanceCount", c_u64),
+        ("TlasNodes", c_vp), ("TlasNodeCount", c_u64),
+        ("MeshTransforms", c_vp), ("MeshTransformCount", c_u64),
+        ("Meshes", c_vp), ("MeshCount", c_u64),
+        ("Materials", c_vp), ("MaterialCount", c_u64),
+        ("Vertices", c_vp), ("VertexCount", c_u64),
+        ("VertexPositions", c_vp), ("VertexPositionCount", c_u64),
+        ("Lights", c_vp), ("LightCount", c_u64),
+        ("UseTlas", c_i32), ("BlasStackSize", c_i32),
+    ]
+
+
+class IdkPtSkyDesc(ctypes.Structure):
+    _fields_ = [("Color", c_f * 3), ("FaceSize", c_i32), ("Faces", c_vp * 6)]
+
+
+class IdkPtSettings(ctypes.Structure):
+    _fields_ = [("Gpu", IdkPtGpuSettings), ("RayDepth", c_i32), ("SamplesPerPixel", c_i32),
+                ("DoRaySorting", c_i32), ("OutputAOVs", c_i32), ("CollectStats", c_i32)]
+
+
+class IdkPtStats(ctypes.Structure):
+    _fields_ = [("Rays", c_u64), ("BounceRays", c_u64 * IDKPT_MAX_RAY_DEPTH),
+                ("NodePairFetches", c_u64), ("TriangleTests", c_u64), ("InstanceVisits", c_u64), ("Hits", c_u64),
+                ("TotalMs", c_f), ("TraverseMs", c_f), ("ShadeMs", c_f), ("SortMs", c_f), ("OtherMs", c_f),
+                ("KernelLaunches", c_u32), ("TraverseLaunches", c_u32)]
+
+    def as_dict(self):
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "BounceRays"}
+        d["BounceRays"] = [int(v) for v in self.BounceRays]
+        return d
+
+
+IDKPT_IMAGE_RESULT, IDKPT_IMAGE_ALBEDO, IDKPT_IMAGE_NORMAL = 0, 1, 2
+IDKPT_ARRAY_MESH_TRANSFORMS, IDKPT_ARRAY_MESHES, IDKPT_ARRAY_MATERIALS, IDKPT_ARRAY_LIGHTS = 0, 1, 2, 3
+
+# every symbol include/idkpt.h declares
+EXPORTS = [
+    "idkpt_create", "idkpt_destroy", "idkpt_last_error", "idkpt_set_scene", "idkpt_update_range", "idkpt_set_sky",
+    "idkpt_resize", "idkpt_reset_accumulation", "idkpt_accumulated_samples", "idkpt_set_accumulated_samples",
+    "idkpt_compute", "idkpt_read_result", "idkpt_write_result", "idkpt_result_device_ptr", "idkpt_tile_rows",
+    "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_abi_version",
+]
+
+
+def default_settings():
+    """PathTracer defaults: GpuSettings (PathTracer.cs:127-138), RayDepth 7 (:211), SamplesPerPixel 1 (:12)."""
+    s = IdkPtSettings()
+    s.Gpu.FocalLength = 8.0
+    s.Gpu.LenseRadius = 0.0
+    s.Gpu.DoDebugBVHTraversal = 0
+    s.Gpu.DoTraceLights = 0
+    s.Gpu.DoRussianRoulette = 1
+    s.RayDepth = 7
+    s.SamplesPerPixel = 1
+    s.DoRaySorting = 0
+    s.OutputAOVs = 0
+    s.CollectStats = 0
+    return s
+
+
+def scene_desc(scene):
+    """IdkPtSceneDesc borrowing the numpy arrays of a host.Scene. Returns (desc, keepalive)."""
+    keep = []
+
+    def ptr(a):
+        a = np.ascontiguousarray(a)
+        keep.append(a)
+        return a.ctypes.data if len(a) else None
+
+    d = IdkPtSceneDesc()
+    d.BlasNodes, d.BlasNodeCount = ptr(scene.blas_nodes), len(scene.blas_nodes)
+    d.BlasTriangles, d.BlasTriangleCount = ptr(scene.blas_triangles), len(scene.blas_triangles)
+    d.BlasDescs, d.BlasDescCount = ptr(scene.blas_descs), len(scene.blas_descs)
+    d.BlasInstances, d.BlasInstanceCount = ptr(scene.blas_instances), len(scene.blas_instances)
+    d.TlasNodes, d.TlasNodeCount = ptr(scene.tlas_nodes), len(scene.tlas_nodes)
+    d.MeshTransforms, d.MeshTransformCount = ptr(scene.mesh_transforms), len(scene.mesh_transforms)
+    d.Meshes, d.MeshCount = ptr(scene.meshes), len(scene.meshes)
+    d.Materials, d.MaterialCount = ptr(scene.materials), len(scene.materials)
+    d.Vertices, d.VertexCount = ptr(scene.vertices), len(scene.vertices)
+    d.VertexPositions, d.VertexPositionCount = ptr(scene.positions), len(scene.positions)
+    d.Lights, d.LightCount = ptr(scene.lights), len(scene.lights)
+    d.UseTlas = int(scene.use_tlas)
+    d.BlasStackSize = int(scene.blas_stack_size)
+    return d, keep
+
+
+def sky_desc(color=(0.6, 0.7, 0.9)):
+    s = IdkPtSkyDesc()
+    s.Color[0], s.Color[1], s.Color[2] = color
+    s.FaceSize = 0
+    return s
+
+
+_lib = None
+
+
+def load(path=None):
+    """dlopen libidkpt.so and declare signatures. Fails loudly if the library is missing: there is no fallback."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    path = path or _build.LIBIDKPT
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing: build it with `python -m idkengine_b200.build` "
+                           "(libidkpt has no CPU fallback)")
+    L = ctypes.CDLL(path)
+    P = ctypes.POINTER
+    L.idkpt_create.restype = c_i32
+    L.idkpt_create.argtypes = [P(IdkPtCreateInfo), P(c_vp)]
+    L.idkpt_destroy.restype = None
+    L.idkpt_destroy.argtypes = [c_vp]
+    L.idkpt_last_error.restype = ctypes.c_char_p
+    L.idkpt_last_error.argtypes = [c_vp]
+    L.idkpt_set_scene.restype = c_i32
+    L.idkpt_set_scene.argtypes = [c_vp, P(IdkPtSceneDesc)]
+    L.idkpt_update_range.restype = c_i32
+    L.idkpt_update_range.argtypes = [c_vp, c_i32, c_u64, c_u64, c_vp]
+    L.idkpt_set_sky.restype = c_i32
+    L.idkpt_set_sky.argtypes = [c_vp, P(IdkPtSkyDesc)]
+    L.idkpt_resize.restype = c_i32
+    L.idkpt_resize.argtypes = [c_vp, c_i32, c_i32]
+    L.idkpt_reset_accumulation.restype = c_i32
+    L.idkpt_reset_accumulation.argtypes = [c_vp]
+    L.idkpt_accumulated_samples.restype = c_u32
+    L.idkpt_accumulated_samples.argtypes = [c_vp]
+    L.idkpt_set_accumulated_samples.restype = c_i32
+    L.idkpt_set_accumulated_samples.argtypes = [c_vp, c_u32]
+    L.idkpt_compute.restype = c_i32
+    L.idkpt_compute.argtypes = [c_vp, c_vp, P(IdkPtSettings), P(IdkPtStats)]
+    L.idkpt_read_result.restype = c_i32
+    L.idkpt_read_result.argtypes = [c_vp, c_i32, c_vp, c_u64]
+    L.idkpt_write_result.restype = c_i32
+    L.idkpt_write_result.argtypes = [c_vp, c_i32, c_vp, c_u64]
+    L.idkpt_result_device_ptr.restype = c_i32
+    L.idkpt_result_device_ptr.argtypes = [c_vp, c_i32, P(c_vp), P(c_u64)]
+    L.idkpt_tile_rows.restype = c_i32
+    L.idkpt_tile_rows.argtypes = [c_vp, P(c_i32), c_vp, c_i32]
+    L.idkpt_read_wavefront_rays.restype = c_i32
+    L.idkpt_read_wavefront_rays.argtypes = [c_vp, c_vp, c_u64]
+    L.idkpt_trace_rays.restype = c_i32
+    L.idkpt_trace_rays.argtypes = [c_vp, c_vp, c_u64, c_i32, c_vp, P(c_f)]
+    L.idkpt_abi_version.restype = c_u32
+    L.idkpt_abi_version.argtypes = []
+    if path == _build.LIBIDKPT:
+        _lib = L
+    return L

@@ -1,0 +1,192 @@
+/*
+ * idkpt.h -- C ABI of libidkpt, the B200-native replacement for the body of
+ * IDKEngine.Render.PathTracer (reference: IDKEngine/Source/Render/PathTracer.cs).
+ *
+ * The C# class keeps its public surface (ctor / Compute / SetSize /
+ * ResetAccumulation / properties, PathTracer.cs:10-125,170-346); its GL
+ * dispatch sequence (PathTracer.cs:214-297) is replaced by P/Invoke calls into
+ * the functions below (binding shown in INTEGRATION.md). Scene data that the
+ * reference binds implicitly to fixed SSBO/UBO slots (ModelManager.cs:103-119,
+ * BVH.cs:145-152, LightManager.cs:80) is handed over explicitly, in the same
+ * struct layouts (idk_gpu_types.h).
+ *
+ * Conventions (mirroring the reference's own native interop, SRC/OIDN/OIDN.cs:
+ * opaque handles, plain pointers + sizes, error string getter):
+ *   - every function returns IDKPT_OK (0) or a negative IdkPtStatus;
+ *   - idkpt_last_error() returns a UTF-8 string owned by the library;
+ *   - host arrays are borrowed only for the duration of the call (copied);
+ *   - a context is single-threaded (the engine's render thread);
+ *   - there is NO CPU fallback: without a usable CUDA device idkpt_create fails.
+ */
+#ifndef IDKPT_H
+#define IDKPT_H
+
+#include "idk_gpu_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define IDKPT_API __declspec(dllexport)
+#else
+#define IDKPT_API __attribute__((visibility("default")))
+#endif
+
+typedef struct IdkPtCtx IdkPtCtx;
+
+typedef enum IdkPtStatus {
+    IDKPT_OK = 0,
+    IDKPT_ERR_INVALID_ARGUMENT = -1,
+    IDKPT_ERR_NO_DEVICE = -2,
+    IDKPT_ERR_CUDA = -3,
+    IDKPT_ERR_NO_SCENE = -4,
+    IDKPT_ERR_OUT_OF_MEMORY = -5,
+    IDKPT_ERR_UNSUPPORTED = -6
+} IdkPtStatus;
+
+#define IDKPT_MAX_RAY_DEPTH 64
+
+/* Replaces: new PathTracer(width, height, settings)   (PathTracer.cs:170-212).
+ * Tile fields implement the multi-GPU screen split (one context per GPU):
+ * image rows are cut into stripes of TileStripeHeight rows, stripe s belongs to
+ * context (s % TileCount) == TileIndex. TileCount <= 1 => the whole image. */
+typedef struct IdkPtCreateInfo {
+    int32_t Device;            /* CUDA device ordinal */
+    int32_t Width;
+    int32_t Height;
+    int32_t TileStripeHeight;  /* rows per stripe (multiple of 8), 0 => 8 */
+    int32_t TileIndex;
+    int32_t TileCount;
+    uint32_t Flags;            /* reserved, 0 */
+} IdkPtCreateInfo;
+
+/* Replaces the implicit SSBO bindings 4,5(vertices),8,9..: ModelManager.cs:103-119
+ * (meshes, materials, vertices, positions, transforms) and BVH.cs:145-152,445-451
+ * (nodes, triangles, descs, instances, tlas) plus LightManager.cs:80 (UBO 2). */
+typedef struct IdkPtSceneDesc {
+    const GpuBlasNode*      BlasNodes;       uint64_t BlasNodeCount;
+    const GpuBlasTriangle*  BlasTriangles;   uint64_t BlasTriangleCount;
+    const GpuBlasDesc*      BlasDescs;       uint64_t BlasDescCount;
+    const GpuBlasInstance*  BlasInstances;   uint64_t BlasInstanceCount;
+    const GpuTlasNode*      TlasNodes;       uint64_t TlasNodeCount;     /* may be NULL/0 */
+    const GpuMeshTransform* MeshTransforms;  uint64_t MeshTransformCount;
+    const GpuMesh*          Meshes;          uint64_t MeshCount;
+    const GpuMaterial*      Materials;       uint64_t MaterialCount;
+    const GpuVertex*        Vertices;        uint64_t VertexCount;
+    const PackedVec3*       VertexPositions; uint64_t VertexPositionCount;
+    const GpuLight*         Lights;          uint64_t LightCount;        /* <= 256 */
+    int32_t UseTlas;        /* BVH.GpuUseTlas (BVH.cs:18-27); default 0 */
+    int32_t BlasStackSize;  /* BVH.BlasStackSize (BVH.cs:29-45,559-567) = max RequiredStackSize */
+} IdkPtSceneDesc;
+
+typedef enum IdkPtArrayId {
+    IDKPT_ARRAY_MESH_TRANSFORMS = 0,
+    IDKPT_ARRAY_MESHES = 1,
+    IDKPT_ARRAY_MATERIALS = 2,
+    IDKPT_ARRAY_LIGHTS = 3
+} IdkPtArrayId;
+
+/* Replaces SkyBoxManager's bindless samplerCube in UBO 5 (SkyBoxManager.cs:87):
+ * either a constant colour or six rgba32f faces (+X,-X,+Y,-Y,+Z,-Z), FaceSize^2
+ * texels each, sampled with nearest filtering. */
+typedef struct IdkPtSkyDesc {
+    float        Color[3];
+    int32_t      FaceSize;       /* 0 => constant Color */
+    const float* Faces[6];
+} IdkPtSkyDesc;
+
+/* PathTracer's runtime-mutable properties (PathTracer.cs:12-125). */
+typedef struct IdkPtSettings {
+    IdkPtGpuSettings Gpu;        /* FocalLength.. DoRussianRoulette */
+    int32_t RayDepth;            /* default 7 (PathTracer.cs:211) */
+    int32_t SamplesPerPixel;     /* default 1 (PathTracer.cs:12) */
+    int32_t DoRaySorting;        /* default 0 (PathTracer.cs:173) */
+    int32_t OutputAOVs;          /* default 0 (PathTracer.cs:174) */
+    int32_t CollectStats;        /* count node-pair fetches / triangle tests (debugCost semantics, BVHIntersect.glsl:45,60) */
+} IdkPtSettings;
+
+typedef struct IdkPtStats {
+    uint64_t Rays;                               /* TraceRay invocations of this call */
+    uint64_t BounceRays[IDKPT_MAX_RAY_DEPTH];    /* per bounce, summed over samples */
+    uint64_t NodePairFetches;                    /* S (valid if CollectStats) */
+    uint64_t TriangleTests;                      /* T (valid if CollectStats) */
+    uint64_t InstanceVisits;                     /* I (valid if CollectStats) */
+    uint64_t Hits;                               /* rays that hit scene geometry (valid if CollectStats) */
+    float    TotalMs;                            /* CUDA-event time of the whole call */
+    float    TraverseMs;                         /* sum over traversal launches */
+    float    ShadeMs;                            /* sum over shade launches */
+    float    SortMs;
+    float    OtherMs;                            /* ray-gen + accumulate */
+    uint32_t KernelLaunches;
+    uint32_t TraverseLaunches;
+} IdkPtStats;
+
+typedef enum IdkPtImage {
+    IDKPT_IMAGE_RESULT = 0,   /* PathTracer.Result        (PathTracer.cs:143) */
+    IDKPT_IMAGE_ALBEDO = 1,   /* PathTracer.AlbedoTexture (PathTracer.cs:167) */
+    IDKPT_IMAGE_NORMAL = 2    /* PathTracer.NormalTexture (PathTracer.cs:168) */
+} IdkPtImage;
+
+/* One ray / hit record of the stand-alone closest-hit query (the GPU analogue of
+ * BVH.Intersect(in Ray, out RayHitInfo), SRC/Bvh/BVH.cs:162-193, with the GLSL
+ * acceptance rules of SH/include/BVHIntersect.glsl:183-291). */
+typedef struct IdkPtRay {
+    float Origin[3];
+    float TMax;
+    float Direction[3];
+    float _pad0;
+} IdkPtRay;
+IDK_STATIC_ASSERT(sizeof(IdkPtRay) == 32, "IdkPtRay must be 32 bytes");
+
+typedef struct IdkPtHit {
+    float    BaryX, BaryY;      /* HitInfo.BaryXY (BVHIntersect.glsl:10-16) */
+    float    T;                 /* == TMax on miss */
+    uint32_t TriangleId;        /* global index into BlasTriangles, ~0u on miss / light */
+    uint32_t MeshTransformId;   /* or light index when TriangleId == ~0u and T < TMax */
+    uint32_t NodePairFetches;   /* per-ray S */
+    uint32_t TriangleTests;     /* per-ray T */
+    uint32_t _pad0;
+} IdkPtHit;
+IDK_STATIC_ASSERT(sizeof(IdkPtHit) == 32, "IdkPtHit must be 32 bytes");
+
+IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out);
+IDKPT_API void idkpt_destroy(IdkPtCtx* ctx);                                  /* PathTracer.Dispose, PathTracer.cs:344 */
+IDKPT_API const char* idkpt_last_error(IdkPtCtx* ctx);                        /* ctx may be NULL: error of the last failed create */
+
+IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* scene);    /* ModelManager.Add -> UpdateBuffers + BVH.BlasesBuild uploads (ModelManager.cs:207-213, BVH.cs:445-451) */
+IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t first, uint64_t count, const void* data); /* dirty-range uploads, ModelManager.cs:236-261; LightManager.cs:363-380 */
+IDKPT_API int idkpt_set_sky(IdkPtCtx* ctx, const IdkPtSkyDesc* sky);
+
+IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height);     /* PathTracer.SetSize, PathTracer.cs:299-332 */
+IDKPT_API int idkpt_reset_accumulation(IdkPtCtx* ctx);                        /* PathTracer.ResetAccumulation, PathTracer.cs:334 */
+IDKPT_API uint32_t idkpt_accumulated_samples(IdkPtCtx* ctx);                  /* PathTracer.AccumulatedSamples, PathTracer.cs:27-37 */
+IDKPT_API int idkpt_set_accumulated_samples(IdkPtCtx* ctx, uint32_t n);       /* restore a snapshot taken with idkpt_read_result */
+
+/* PathTracer.Compute(), PathTracer.cs:214-271. Images stay on the device.
+ * stats may be NULL. Synchronous w.r.t. the returned stats. */
+IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const IdkPtSettings* settings, IdkPtStats* stats);
+
+/* Host read-back / restore of an rgba32f image of this context's tile rows in
+ * full-image layout (rows not owned by the tile are left untouched). */
+IDKPT_API int idkpt_read_result(IdkPtCtx* ctx, IdkPtImage which, void* dst_rgba32f, uint64_t bytes);
+IDKPT_API int idkpt_write_result(IdkPtCtx* ctx, IdkPtImage which, const void* src_rgba32f, uint64_t bytes);
+
+/* Device-side access for zero-copy hand-over (GL interop / NCCL gather):
+ * pointer to this tile's compact rgba32f rows (TileRowCount*Width float4). */
+IDKPT_API int idkpt_result_device_ptr(IdkPtCtx* ctx, IdkPtImage which, void** dev_ptr, uint64_t* bytes);
+IDKPT_API int idkpt_tile_rows(IdkPtCtx* ctx, int32_t* row_count, int32_t* rows_out, int32_t capacity);
+
+/* Export the wavefront state of the last compute() call in the reference's
+ * per-pixel layout (GpuWavefrontRay[W*H], SSBO 30) for inspection / parity. */
+IDKPT_API int idkpt_read_wavefront_rays(IdkPtCtx* ctx, GpuWavefrontRay* dst, uint64_t count);
+
+/* Stand-alone closest-hit batch with host buffers (H2D + kernel + D2H inside). */
+IDKPT_API int idkpt_trace_rays(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, int32_t trace_lights, IdkPtHit* hits_out, float* kernel_ms);
+
+IDKPT_API uint32_t idkpt_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* IDKPT_H */
