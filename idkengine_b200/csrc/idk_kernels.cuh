@@ -1,0 +1,691 @@
+// Wavefront path-tracing kernels for sm_100a (B200). See DESIGN.md for the HBM layout and the
+// algorithmic-byte accounting of each kernel.
+//
+//   k_prepare_triangles  scene upload: 48-byte triangle records (p0,e1,e2,n) from indices+positions
+//   k_raygen             FirstHit/compute.glsl:44-81   ray generation (camera, jitter, thin lens)
+//   k_traverse           BVHIntersect.glsl:27-105,183-291  closest hit, persistent warps + dynamic fetch
+//   k_shade              FirstHit/compute.glsl:100-234, NHit/compute.glsl:91-215 + ordered compaction
+//   k_accumulate         FinalDraw/compute.glsl:24-62
+//   k_trace_rays         stand-alone closest-hit batch (BVH.Intersect analogue)
+#pragma once
+#include "idk_device.cuh"
+#include "../../include/idk_gpu_types.h"
+
+#define IDK_BLOCK 256
+#define IDK_WARPS (IDK_BLOCK / 32)
+
+struct DeviceScene {
+    const float4* nodes;          // 2 x float4 per GpuBlasNode
+    const float4* triRec;         // 3 x float4 per triangle: (p0.xyz,e1.x) (e1.yz,e2.xy) (e2.z,n.xyz)
+    const int4* blasTris;         // GpuBlasTriangle
+    const GpuBlasDesc* descs;
+    const GpuBlasInstance* instances;
+    const float4* xforms;         // 9 x float4 per GpuMeshTransform
+    const GpuMesh* meshes;
+    const GpuMaterial* materials;
+    const uint4* vertices;        // GpuVertex
+    const GpuLight* lights;
+    uint32_t instanceCount;
+    uint32_t lightCount;
+    float skyR, skyG, skyB;
+    int stackSize;
+};
+
+// 64-byte per-slot path state (slot = position in the alive list of the current bounce).
+struct __align__(16) PathState {
+    float ox, oy, oz, prevIor;     // Origin, PreviousIOROrTraverseCost
+    float pdx, pdy;                // PackedDirectionX/Y (octahedral)
+    uint32_t pix;                  // tile-local ray index (y_local * W + x)
+    uint32_t reseed;               // FirstHit only: gl_GlobalInvocationID.y*4096 + .x (un-swizzled)
+    float tx, ty, tz;              // Throughput
+    uint32_t rng;                  // FirstHit only: RNG state after ray generation
+    float rx, ry, rz;              // Radiance
+    uint32_t pad;
+};
+static_assert(sizeof(PathState) == 64, "PathState must be 64 bytes");
+
+struct HitRec { float bx, by, t; uint32_t tri; };   // 16 bytes, + uint32 transform id in a second array
+
+struct TraceCounters { unsigned long long steps, tris, instances, hits; };
+
+// ------------------------------------------------------------------------------------------------
+__global__ void k_prepare_triangles(const int4* __restrict__ tris, const float* __restrict__ positions,
+                                    float4* __restrict__ triRec, uint32_t count) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    int4 t = tris[i];
+    f3 p0 = mk3(positions[3 * t.x], positions[3 * t.x + 1], positions[3 * t.x + 2]);
+    f3 p1 = mk3(positions[3 * t.y], positions[3 * t.y + 1], positions[3 * t.y + 2]);
+    f3 p2 = mk3(positions[3 * t.z], positions[3 * t.z + 1], positions[3 * t.z + 2]);
+    f3 e1 = p1 - p0, e2 = p2 - p0;
+    f3 n = cross3(e1, e2);
+    triRec[3 * (size_t)i + 0] = make_float4(p0.x, p0.y, p0.z, e1.x);
+    triRec[3 * (size_t)i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
+    triRec[3 * (size_t)i + 2] = make_float4(e2.z, n.x, n.y, n.z);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Closest-hit traversal of one ray. `stack` points at this thread's column of the shared stack
+// (stride IDK_BLOCK), exactly the reference's `shared uint BlasTraversalStack[SIZE][LOCAL_SIZE]`.
+template <bool STATS>
+__device__ __forceinline__ void trace_closest(const DeviceScene& sc, f3 o, f3 d, float tMax, bool traceLights,
+                                              uint32_t* stack, HitRec& hit, uint32_t& hitXform,
+                                              uint32_t& S, uint32_t& T, uint32_t& I, float& cost) {
+    hit.t = tMax;
+    hit.tri = ~0u;
+    hit.bx = 0.0f;
+    hit.by = 0.0f;
+    hitXform = 0;
+
+    if (traceLights) {
+        for (uint32_t i = 0; i < sc.lightCount; i++) {
+            const GpuLight& L = sc.lights[i];
+            float tMin, tMx;
+            if (ray_sphere(o, d, mk3(L.Position[0], L.Position[1], L.Position[2]), L.Radius, tMin, tMx) && tMin < hit.t) {
+                hit.t = tMin < 0.0f ? tMx : tMin;
+                hitXform = i;
+                hit.tri = ~0u;
+            }
+        }
+    }
+
+    for (uint32_t inst = 0; inst < sc.instanceCount; inst++) {
+        const GpuBlasInstance bi = sc.instances[inst];
+        const int nodeOffset = sc.descs[bi.BlasId].NodeOffset;
+        const uint32_t triOffset = (uint32_t)sc.descs[bi.BlasId].TriangleOffset;
+        const float4* xf = sc.xforms + 9 * (size_t)bi.MeshTransformId + 3;   // InvModelMatrix rows
+        const float4 r0 = ldg4(xf), r1 = ldg4(xf + 1), r2 = ldg4(xf + 2);
+        const f3 lo = xform_point(r0, r1, r2, o);
+        const f3 ld = xform_vector(r0, r1, r2, d);
+        const f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+        const float4* nodes = sc.nodes + 2 * (size_t)nodeOffset;
+        if (STATS) I++;
+
+        float tMinLeft, tMinRight;
+        {
+            const float4 a = ldg4(nodes + 2), b = ldg4(nodes + 3);   // root = node 1
+            if (!(ray_box(lo, inv, a, b, tMinLeft) && tMinLeft < hit.t)) continue;
+        }
+
+        bool blasHit = false;
+        uint32_t sp = 0;
+        uint32_t top = 2;
+        while (true) {
+            if (STATS) { S++; cost += 1.0f; }
+            const float4* np = nodes + 2 * (size_t)top;
+            const float4 lA = ldg4(np), lB = ldg4(np + 1), rA = ldg4(np + 2), rB = ldg4(np + 3);
+            const int lChild = __float_as_int(lA.w), lCount = __float_as_int(lB.w);
+            const int rChild = __float_as_int(rA.w), rCount = __float_as_int(rB.w);
+
+            const bool hitLeft = ray_box(lo, inv, lA, lB, tMinLeft) && tMinLeft <= hit.t;
+            const bool hitRight = ray_box(lo, inv, rA, rB, tMinRight) && tMinRight <= hit.t;
+
+            const bool intersectLeft = hitLeft && lCount > 0;
+            const bool intersectRight = hitRight && rCount > 0;
+            if (intersectLeft || intersectRight) {
+                uint32_t first = intersectLeft ? (uint32_t)lChild : (uint32_t)rChild;
+                uint32_t end = !intersectRight ? (uint32_t)(lChild + lCount) : (uint32_t)(rChild + rCount);
+                first += triOffset;
+                end += triOffset;
+                if (STATS) { T += end - first; cost += (float)(end - first) * 1.1f; }
+                for (uint32_t i = first; i < end; i++) {
+                    const float4* tr = sc.triRec + 3 * (size_t)i;
+                    const float4 a = ldg4(tr), b = ldg4(tr + 1), c = ldg4(tr + 2);
+                    float bx, by, t;
+                    if (ray_triangle(lo, ld, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), bx, by, t) && t < hit.t) {
+                        blasHit = true;
+                        hit.tri = i;
+                        hit.bx = bx;
+                        hit.by = by;
+                        hit.t = t;
+                    }
+                }
+            }
+
+            const bool traverseLeft = hitLeft && lCount == 0;
+            const bool traverseRight = hitRight && rCount == 0;
+            if (traverseLeft || traverseRight) {
+                if (traverseLeft && traverseRight) {
+                    const bool leftCloser = tMinLeft < tMinRight;
+                    top = leftCloser ? (uint32_t)lChild : (uint32_t)rChild;
+                    stack[(sp++) * IDK_BLOCK] = leftCloser ? (uint32_t)rChild : (uint32_t)lChild;
+                } else {
+                    top = traverseLeft ? (uint32_t)lChild : (uint32_t)rChild;
+                }
+            } else {
+                if (sp == 0) break;
+                top = stack[(--sp) * IDK_BLOCK];
+            }
+        }
+        if (blasHit) hitXform = bi.MeshTransformId;
+    }
+}
+
+struct TraverseArgs {
+    DeviceScene sc;
+    const PathState* state;        // indexed by perm[gid] (or gid)
+    const uint32_t* perm;          // may be null
+    const uint32_t* count;         // alive count of this bounce (device)
+    uint32_t* ticket;              // dynamic fetch counter (zeroed per launch)
+    HitRec* hits;                  // by gid
+    uint32_t* hitXform;            // by gid
+    float* debugCost;              // by gid, STATS only
+    TraceCounters* counters;       // STATS only
+    int traceLights;
+};
+
+// Persistent warps: every warp repeatedly claims 32 consecutive slots of the alive list.
+template <bool STATS>
+__global__ void __launch_bounds__(IDK_BLOCK) k_traverse(TraverseArgs a) {
+    extern __shared__ uint32_t s_stack[];
+    uint32_t* stack = s_stack + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t count = *a.count;
+    uint32_t S = 0, T = 0, I = 0, H = 0;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.ticket, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= count) break;
+        const uint32_t gid = base + lane;
+        if (gid < count) {
+            const uint32_t src = a.perm ? a.perm[gid] : gid;
+            const float4* sp = reinterpret_cast<const float4*>(a.state + src);
+            const float4 s0 = sp[0], s1 = sp[1];
+            const f3 o = mk3(s0.x, s0.y, s0.z);
+            const f3 d = decode_unit_vec(s1.x, s1.y);
+            HitRec hit;
+            uint32_t xf;
+            float cost = 0.0f;
+            trace_closest<STATS>(a.sc, o, d, IDK_FLOAT_MAX, a.traceLights != 0, stack, hit, xf, S, T, I, cost);
+            reinterpret_cast<float4*>(a.hits)[gid] = make_float4(hit.bx, hit.by, hit.t, __uint_as_float(hit.tri));
+            a.hitXform[gid] = xf;
+            if (STATS) {
+                a.debugCost[gid] = cost;
+                if (hit.tri != ~0u) H++;
+            }
+        }
+    }
+    if (STATS) {
+        for (int off = 16; off > 0; off >>= 1) {
+            S += __shfl_down_sync(0xffffffffu, S, off);
+            T += __shfl_down_sync(0xffffffffu, T, off);
+            I += __shfl_down_sync(0xffffffffu, I, off);
+            H += __shfl_down_sync(0xffffffffu, H, off);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.counters->steps, (unsigned long long)S);
+            atomicAdd(&a.counters->tris, (unsigned long long)T);
+            atomicAdd(&a.counters->instances, (unsigned long long)I);
+            atomicAdd(&a.counters->hits, (unsigned long long)H);
+        }
+    }
+}
+
+// Stand-alone batch: rays in, hits out (IdkPtRay / IdkPtHit of idkpt.h), per-ray S/T always reported.
+struct TraceRaysArgs {
+    DeviceScene sc;
+    const float4* rays;   // 2 x float4 per ray
+    uint4* hits;          // 2 x uint4 per hit
+    uint32_t count;
+    uint32_t* ticket;
+    int traceLights;
+};
+
+__global__ void __launch_bounds__(IDK_BLOCK) k_trace_rays(TraceRaysArgs a) {
+    extern __shared__ uint32_t s_stack[];
+    uint32_t* stack = s_stack + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    for (;;) {
+        uint32_t base = 0;
+        if (lane == 0) base = atomicAdd(a.ticket, 32u);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (base >= a.count) break;
+        const uint32_t gid = base + lane;
+        if (gid < a.count) {
+            const float4 r0 = a.rays[2 * (size_t)gid], r1 = a.rays[2 * (size_t)gid + 1];
+            HitRec hit;
+            uint32_t xf, S = 0, T = 0, I = 0;
+            float cost = 0.0f;
+            trace_closest<true>(a.sc, mk3(r0.x, r0.y, r0.z), mk3(r1.x, r1.y, r1.z), r0.w, a.traceLights != 0, stack, hit, xf, S, T, I, cost);
+            a.hits[2 * (size_t)gid] = make_uint4(__float_as_uint(hit.bx), __float_as_uint(hit.by), __float_as_uint(hit.t), hit.tri);
+            a.hits[2 * (size_t)gid + 1] = make_uint4(xf, S, T, 0u);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+struct FrameParams {
+    float invProj[16];
+    float invView[16];
+    float viewPos[3];
+    float focalLength, lenseRadius;
+    int width, height;             // full image
+    int stripeH, tileIndex, tileCount;
+    uint32_t accumulatedSamples;
+    int doDebugTraversal, doTraceLights, doRussianRoulette;
+};
+
+__device__ __forceinline__ bool tile_owns_row(const FrameParams& f, int y, int& localRow) {
+    const int stripe = y / f.stripeH;
+    if (f.tileCount > 1 && (stripe % f.tileCount) != f.tileIndex) return false;
+    localRow = (f.tileCount > 1 ? (stripe / f.tileCount) : stripe) * f.stripeH + (y % f.stripeH);
+    return true;
+}
+
+// One thread per (un-swizzled) invocation of the reference's 8x8 FirstHit dispatch.
+__global__ void __launch_bounds__(64) k_raygen(FrameParams f, PathState* __restrict__ state) {
+    // ReorderInvocations(20), FirstHit/compute.glsl:236-262
+    const uint32_t n = 20;
+    const uint32_t idx = blockIdx.y * gridDim.x + blockIdx.x;
+    const uint32_t columnSize = gridDim.y * n;
+    const uint32_t fullColumnCount = gridDim.x / n;
+    const uint32_t lastColumnWidth = gridDim.x % n;
+    const uint32_t columnIdx = idx / columnSize;
+    const uint32_t idxInColumn = idx % columnSize;
+    uint32_t columnWidth = n;
+    if (columnIdx == fullColumnCount) columnWidth = lastColumnWidth;
+    const uint32_t swy = idxInColumn / columnWidth;
+    const uint32_t swx = idxInColumn % columnWidth + columnIdx * n;
+    const int x = (int)(swx * 8 + threadIdx.x), y = (int)(swy * 8 + threadIdx.y);
+    if (x >= f.width || y >= f.height) return;
+    int localRow;
+    if (!tile_owns_row(f, y, localRow)) return;
+
+    const uint32_t gidX = blockIdx.x * 8 + threadIdx.x, gidY = blockIdx.y * 8 + threadIdx.y;
+    uint32_t seed = (uint32_t)(y * 4096 + x) * (f.accumulatedSamples + 1u);
+    const float sx = rnd01(seed), sy = rnd01(seed);
+    const float ndcx = ((float)x + sx) / (float)f.width * 2.0f - 1.0f;
+    const float ndcy = ((float)y + sy) / (float)f.height * 2.0f - 1.0f;
+    const float rvx = f.invProj[0] * ndcx + f.invProj[4] * ndcy;
+    const float rvy = f.invProj[1] * ndcx + f.invProj[5] * ndcy;
+    f3 camDir = normalize3(mat4_mul_xyz(f.invView, rvx, rvy, -1.0f, 0.0f));
+    const f3 focalPoint = mk3(f.viewPos[0], f.viewPos[1], f.viewPos[2]) + camDir * f.focalLength;
+    float dx, dy;
+    sample_disk(seed, dx, dy);
+    const f3 pointOnLense = mat4_mul_xyz(f.invView, f.lenseRadius * dx, f.lenseRadius * dy, 0.0f, 1.0f);
+    camDir = normalize3(focalPoint - pointOnLense);
+
+    float pdx, pdy;
+    encode_unit_vec(camDir, pdx, pdy);
+    const uint32_t li = (uint32_t)localRow * (uint32_t)f.width + (uint32_t)x;
+    float4* out = reinterpret_cast<float4*>(state + li);
+    out[0] = make_float4(pointOnLense.x, pointOnLense.y, pointOnLense.z, 1.0f);
+    out[1] = make_float4(pdx, pdy, __uint_as_float(li), __uint_as_float(gidY * 4096u + gidX));
+    out[2] = make_float4(1.0f, 1.0f, 1.0f, __uint_as_float(seed));
+    out[3] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+}
+
+// ------------------------------------------------------------------------------------------------
+struct Surface {
+    f3 Albedo; float Alpha;
+    f3 Normal, Emissive, Absorbance;
+    float Metallic, Roughness, Transmission, IOR, AlphaCutoff;
+    bool IsVolumetric, TintOnTransmissive;
+};
+
+struct ShadeArgs {
+    DeviceScene sc;
+    FrameParams f;
+    const PathState* stateIn;      // by perm[gid] / gid
+    PathState* stateOut;           // by new slot
+    const float4* aovIn;           // 2 x float4 per slot (by perm[gid] / gid)
+    float4* aovOut;
+    const uint32_t* perm;          // may be null
+    const HitRec* hits;            // by gid
+    const uint32_t* hitXform;
+    const float* debugCost;        // by gid (debug traversal only)
+    const uint32_t* count;         // alive count in
+    uint32_t* countOut;            // alive count out (pre-zeroed)
+    uint32_t* ticket;              // tile ticket (pre-zeroed)
+    unsigned long long* tileStatus;// decoupled look-back status words, tagged with epoch
+    uint32_t epoch;
+    uint32_t* keysOut;             // sort key per new slot (ray sorting only), may be null
+    float4* radiance;              // per tile pixel: final radiance (w = traversal cost)
+    float4* aovAlbedoFinal;        // per tile pixel (AOVs only)
+    float4* aovNormalFinal;
+    GpuWavefrontRay* exportRays;   // per tile pixel, reference layout (debug export), may be null
+    int firstHit;
+    int lastBounce;                // survivors are final: no compaction
+    int outputAovs;
+};
+
+// status word: [63:34] epoch, [33:32] flag (1 = aggregate, 2 = inclusive prefix), [31:0] value
+__device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, uint32_t flag, uint32_t value) {
+    return ((unsigned long long)epoch << 34) | ((unsigned long long)flag << 32) | value;
+}
+
+__global__ void __launch_bounds__(IDK_BLOCK) k_shade(ShadeArgs a) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warpCount[IDK_WARPS];
+    __shared__ uint32_t s_base;
+    const uint32_t count = *a.count;
+    const uint32_t numTiles = (count + IDK_BLOCK - 1) / IDK_BLOCK;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const DeviceScene& sc = a.sc;
+    const FrameParams& f = a.f;
+
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= numTiles) break;
+        const uint32_t gid = tile * IDK_BLOCK + threadIdx.x;
+        bool survive = false;
+        PathState st;
+        float4 aov0 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), aov1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        uint32_t sortingKey = 0;
+
+        if (gid < count) {
+            const uint32_t src = a.perm ? a.perm[gid] : gid;
+            {
+                const float4* sp = reinterpret_cast<const float4*>(a.stateIn + src);
+                float4 v0 = sp[0], v1 = sp[1], v2 = sp[2], v3 = sp[3];
+                st.ox = v0.x; st.oy = v0.y; st.oz = v0.z; st.prevIor = v0.w;
+                st.pdx = v1.x; st.pdy = v1.y; st.pix = __float_as_uint(v1.z); st.reseed = __float_as_uint(v1.w);
+                st.tx = v2.x; st.ty = v2.y; st.tz = v2.z; st.rng = __float_as_uint(v2.w);
+                st.rx = v3.x; st.ry = v3.y; st.rz = v3.z; st.pad = 0;
+            }
+            if (a.outputAovs && !a.firstHit) { aov0 = a.aovIn[2 * (size_t)src]; aov1 = a.aovIn[2 * (size_t)src + 1]; }
+            uint32_t rng = a.firstHit ? st.rng : (gid * 4096u + f.accumulatedSamples);
+            const uint32_t reseed = a.firstHit ? st.reseed : gid;   // gl_GlobalInvocationID.y*4096 + .x
+
+            const float4 hv = reinterpret_cast<const float4*>(a.hits)[gid];
+            const float hitT = hv.z;
+            const uint32_t hitTri = __float_as_uint(hv.w);
+            const uint32_t hitXf = a.hitXform[gid];
+            const bool hitScene = hitT != IDK_FLOAT_MAX;
+            const f3 rayDir = decode_unit_vec(st.pdx, st.pdy);
+            f3 origin = mk3(st.ox, st.oy, st.oz);
+            f3 thr = mk3(st.tx, st.ty, st.tz);
+            f3 rad = mk3(st.rx, st.ry, st.rz);
+
+            if (a.firstHit && f.doDebugTraversal) {
+                st.prevIor = a.debugCost[gid];
+                survive = false;
+            } else if (hitScene) {
+                origin = origin + rayDir * hitT;
+                Surface s;
+                s.Albedo = mk3(1.0f, 1.0f, 1.0f); s.Alpha = 1.0f;
+                s.Normal = mk3(0.0f, 0.0f, 0.0f); s.Emissive = mk3(0.0f, 0.0f, 0.0f); s.Absorbance = mk3(0.0f, 0.0f, 0.0f);
+                s.Metallic = 0.0f; s.Roughness = 0.0f; s.Transmission = 0.0f; s.IOR = 1.5f; s.AlphaCutoff = 0.5f;
+                s.IsVolumetric = false; s.TintOnTransmissive = true;
+                f3 geometricNormal = mk3(0.0f, 0.0f, 0.0f);
+                bool passThrough = false;
+                const bool hitLight = hitTri == ~0u;
+                if (!hitLight) {
+                    sortingKey = hitTri;
+                    const int4 tri = __ldg(sc.blasTris + hitTri);
+                    const uint4 v0 = __ldg(sc.vertices + tri.x), v1 = __ldg(sc.vertices + tri.y), v2 = __ldg(sc.vertices + tri.z);
+                    const float b0 = hv.x, b1 = hv.y, b2 = 1.0f - hv.x - hv.y;
+                    const f3 interpNormal = normalize3((decompress_sr11g11b10(v0.w) * b0 + decompress_sr11g11b10(v1.w) * b1) + decompress_sr11g11b10(v2.w) * b2);
+                    const f3 interpTangent = normalize3((decompress_sr11g11b10(v0.z) * b0 + decompress_sr11g11b10(v1.z) * b1) + decompress_sr11g11b10(v2.z) * b2);
+                    const float4* xf = sc.xforms + 9 * (size_t)hitXf + 3;
+                    const float4 r0 = ldg4(xf), r1 = ldg4(xf + 1), r2 = ldg4(xf + 2);
+                    const GpuMesh& mesh = sc.meshes[tri.w];
+                    const GpuMaterial& mat = sc.materials[mesh.MaterialId];
+
+                    // GetSurface with 1x1 white textures (Surface.glsl:49-77)
+                    const uint32_t c = mat.BaseColorFactor;
+                    s.Albedo = mk3((float)(c & 255u) / 255.0f, (float)((c >> 8) & 255u) / 255.0f, (float)((c >> 16) & 255u) / 255.0f);
+                    s.Alpha = (float)((c >> 24) & 255u) / 255.0f;
+                    s.Normal = mk3(1.0f, 1.0f, 0.0f);
+                    s.Emissive = mk3(mat.EmissiveFactor[0], mat.EmissiveFactor[1], mat.EmissiveFactor[2]);
+                    s.Absorbance = mk3(mat.Absorbance[0], mat.Absorbance[1], mat.Absorbance[2]);
+                    s.Metallic = mat.MetallicFactor;
+                    s.Roughness = mat.RoughnessFactor;
+                    s.Transmission = mat.TransmissionFactor;
+                    s.IOR = mat.IOR;
+                    s.AlphaCutoff = mat.AlphaCutoff;
+                    s.IsVolumetric = mat.IsVolumetric != 0;
+                    // SurfaceApplyModificatons (Surface.glsl:85-96)
+                    s.Emissive = s.Emissive * 1.0f + mesh.EmissiveBias * s.Albedo;
+                    const f3 ab = s.Absorbance + mk3(mesh.AbsorbanceBias[0], mesh.AbsorbanceBias[1], mesh.AbsorbanceBias[2]);
+                    s.Absorbance = mk3(fmaxf(ab.x, 0.0f), fmaxf(ab.y, 0.0f), fmaxf(ab.z, 0.0f));
+                    s.Metallic = clamp1(s.Metallic + mesh.SpecularBias, 0.0f, 1.0f);
+                    s.Roughness = clamp1(s.Roughness + mesh.RoughnessBias, 0.0f, 1.0f);
+                    s.Transmission = clamp1(s.Transmission + mesh.TransmissionBias, 0.0f, 1.0f);
+                    s.IOR = fmaxf(s.IOR + mesh.IORBias, 1.0f);
+                    s.TintOnTransmissive = mesh.TintOnTransmissive != 0;
+
+                    const float alphaCutoff = (s.AlphaCutoff == 2.0f) ? rnd01(rng) : s.AlphaCutoff;
+                    if (s.Alpha < alphaCutoff) {
+                        origin = origin + rayDir * 0.001f;
+                        passThrough = true;
+                    } else {
+                        const f3 worldNormal = normalize3(xform_normal(r0, r1, r2, interpNormal));
+                        const f3 worldTangent = normalize3(xform_normal(r0, r1, r2, interpTangent));
+                        const f3 N = normalize3(worldNormal);
+                        const f3 T = normalize3(worldTangent);
+                        const f3 B = normalize3(cross3(N, T));
+                        const f3 tbnN = (T * s.Normal.x + B * s.Normal.y) + N * s.Normal.z;
+                        s.Normal = normalize3(mix3(worldNormal, tbnN, mesh.NormalMapStrength));
+                        const float4 tr = ldg4(sc.triRec + 3 * (size_t)hitTri + 2);
+                        geometricNormal = normalize3(mk3(tr.y, tr.z, tr.w));   // GetTriangleNormal
+                        geometricNormal = normalize3(xform_normal(r0, r1, r2, geometricNormal));
+                    }
+                } else if (f.doTraceLights) {
+                    sortingKey = hitXf;
+                    const GpuLight& L = sc.lights[hitXf];
+                    s.Emissive = mk3(L.Color[0], L.Color[1], L.Color[2]);
+                    s.Albedo = s.Emissive;
+                    s.Normal = (origin - mk3(L.Position[0], L.Position[1], L.Position[2])) / L.Radius;
+                    geometricNormal = s.Normal;
+                }
+
+                if (passThrough) {
+                    survive = true;
+                } else {
+                    float prevIor = a.firstHit ? 1.0f : st.prevIor;
+                    const bool fromInside = dot3(-rayDir, geometricNormal) < 0.0f;
+                    if (fromInside) {
+                        if (a.firstHit) prevIor = s.IOR;
+                        geometricNormal = geometricNormal * -1.0f;
+                        if (s.IsVolumetric) {
+                            const f3 e = -s.Absorbance * hitT;
+                            thr = thr * mk3(det_exp(e.x), det_exp(e.y), det_exp(e.z));
+                        }
+                    }
+                    float cosTheta = dot3(-rayDir, s.Normal);
+                    if (cosTheta < 0.0f) s.Normal = s.Normal * -1.0f;
+
+                    rad = rad + s.Emissive * thr;
+
+                    // ---- SampleMaterial (Shading.glsl:52-150)
+                    Surface m = s;
+                    m.Roughness *= m.Roughness;
+                    cosTheta = dot3(-rayDir, m.Normal);
+                    {
+                        const float diffuseChance = 1.0f - m.Metallic - m.Transmission;
+                        const float r0f = (prevIor - m.IOR) / (prevIor + m.IOR);
+                        const float f0 = r0f * r0f;
+                        const float fres = f0 + (1.0f - f0) * pow5f(1.0f - cosTheta);
+                        m.Metallic = mix1(m.Metallic, 1.0f, fres);
+                        m.Transmission = fmaxf(1.0f - diffuseChance - m.Metallic, 0.0f);
+                    }
+                    uint32_t bsdfType;
+                    {
+                        const float rnd = rnd01(rng);
+                        if (m.Metallic > rnd) bsdfType = 1u;
+                        else if (m.Metallic + m.Transmission > rnd) bsdfType = 2u;
+                        else bsdfType = 0u;
+                    }
+                    f3 diffuseRayDir;
+                    {
+                        uint32_t tmp = reseed;
+                        const float g = 1.32471795724474602596f;
+                        const float a1 = 1.0f / g, a2 = 1.0f / (g * g);
+                        const float r2u = fract1((float)f.accumulatedSamples * a1), r2v = fract1((float)f.accumulatedSamples * a2);
+                        const float po0 = rnd01(tmp), po1 = rnd01(tmp);
+                        const float u = fract1(r2u + po0), v = fract1(r2v + po1);
+                        diffuseRayDir = normalize3(m.Normal + sample_sphere(u, v));
+                    }
+                    f3 newDir, bsdf;
+                    float newIor;
+                    if (bsdfType == 0u) {
+                        newDir = diffuseRayDir; newIor = prevIor; bsdf = m.Albedo;
+                    } else if (bsdfType == 1u) {
+                        newDir = normalize3(mix3(reflect3(rayDir, m.Normal), diffuseRayDir, m.Roughness));
+                        bsdf = m.Albedo; newIor = prevIor;
+                    } else {
+                        newIor = fromInside ? 1.0f : m.IOR;
+                        f3 refr;
+                        bool tir;
+                        if (!m.IsVolumetric) {
+                            refr = rayDir; tir = false; newIor = 1.0f;
+                        } else {
+                            refr = refract3(rayDir, m.Normal, prevIor / newIor);
+                            tir = refr.x == 0.0f && refr.y == 0.0f && refr.z == 0.0f;
+                            if (tir) { refr = reflect3(rayDir, m.Normal); newIor = prevIor; }
+                        }
+                        newDir = normalize3(mix3(refr, !tir ? -diffuseRayDir : diffuseRayDir, m.Roughness));
+                        const bool gltfWantsTint = m.IsVolumetric || !fromInside;
+                        bsdf = (gltfWantsTint && m.TintOnTransmissive) ? m.Albedo : mk3(1.0f, 1.0f, 1.0f);
+                    }
+                    const float pdf = fmaxf(1.0f, 0.0001f);
+                    thr = thr * (bsdf / pdf);
+
+                    if (a.outputAovs) {
+                        // GetSurfaceVariance uses the un-remapped surface (FirstHit:197-203)
+                        const float dc = 1.0f - s.Metallic - s.Transmission;
+                        const float weight = dc + s.Metallic * s.Roughness + s.Transmission * s.Roughness;
+                        if (a.firstHit) {
+                            const f3 al = s.Albedo * weight, no = s.Normal * weight;
+                            aov0 = make_float4(al.x, al.y, al.z, 1.0f - weight);
+                            aov1 = make_float4(no.x, no.y, no.z, 0.0f);
+                        } else {
+                            const f3 al = mk3(aov0.x, aov0.y, aov0.z) + aov0.w * s.Albedo * weight;
+                            const f3 no = mk3(aov1.x, aov1.y, aov1.z) + aov0.w * s.Normal * weight;
+                            aov0 = make_float4(al.x, al.y, al.z, aov0.w * (1.0f - weight));
+                            aov1 = make_float4(no.x, no.y, no.z, 0.0f);
+                        }
+                    }
+
+                    bool terminate = false;
+                    if (!a.firstHit && f.doRussianRoulette) {
+                        const float p = fmaxf(thr.x, fmaxf(thr.y, thr.z));
+                        if (rnd01(rng) > p) terminate = true;
+                        else thr = thr / p;
+                    }
+                    if (!terminate) {
+                        if (bsdfType == 2u) geometricNormal = geometricNormal * -1.0f;
+                        origin = origin + geometricNormal * 0.001f;
+                        st.prevIor = newIor;
+                        encode_unit_vec(newDir, st.pdx, st.pdy);
+                        survive = true;
+                    }
+                }
+            } else {
+                const f3 albedo = mk3(sc.skyR, sc.skyG, sc.skyB);
+                if (a.outputAovs) {
+                    const f3 fn = cubemap_face_normal(rayDir);
+                    if (a.firstHit) {
+                        aov0 = make_float4(albedo.x, albedo.y, albedo.z, 0.0f);
+                        aov1 = make_float4(fn.x, fn.y, fn.z, 0.0f);
+                    } else {
+                        const f3 al = mk3(aov0.x, aov0.y, aov0.z) + aov0.w * albedo;
+                        const f3 no = mk3(aov1.x, aov1.y, aov1.z) + aov0.w * fn;
+                        aov0 = make_float4(al.x, al.y, al.z, 0.0f);
+                        aov1 = make_float4(no.x, no.y, no.z, 0.0f);
+                    }
+                }
+                rad = rad + albedo * thr;
+                survive = false;
+            }
+            st.ox = origin.x; st.oy = origin.y; st.oz = origin.z;
+            st.tx = thr.x; st.ty = thr.y; st.tz = thr.z;
+            st.rx = rad.x; st.ry = rad.y; st.rz = rad.z;
+
+            if (!survive || a.lastBounce) {
+                // path is final for this sample: hand its radiance (and AOVs) to the accumulate kernel
+                a.radiance[st.pix] = make_float4(st.rx, st.ry, st.rz, st.prevIor);
+                if (a.outputAovs) { a.aovAlbedoFinal[st.pix] = aov0; a.aovNormalFinal[st.pix] = aov1; }
+                if (a.exportRays) {
+                    GpuWavefrontRay w;
+                    w.Origin[0] = st.ox; w.Origin[1] = st.oy; w.Origin[2] = st.oz; w.PreviousIOROrTraverseCost = st.prevIor;
+                    w.Throughput[0] = st.tx; w.Throughput[1] = st.ty; w.Throughput[2] = st.tz; w.PackedDirectionX = st.pdx;
+                    w.Radiance[0] = st.rx; w.Radiance[1] = st.ry; w.Radiance[2] = st.rz; w.PackedDirectionY = st.pdy;
+                    a.exportRays[st.pix] = w;
+                }
+            }
+        }
+        if (a.lastBounce) continue;
+
+        // ---- ordered compaction: block scan + decoupled look-back across tiles (ascending slot order)
+        const uint32_t ballot = __ballot_sync(0xffffffffu, survive);
+        const uint32_t rankInWarp = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_warpCount[warp] = __popc(ballot);
+        __syncthreads();
+        uint32_t warpOffset = 0, blockTotal = 0;
+#pragma unroll
+        for (int w = 0; w < IDK_WARPS; w++) {
+            const uint32_t c = s_warpCount[w];
+            if (w < (int)warp) warpOffset += c;
+            blockTotal += c;
+        }
+        if (threadIdx.x == 0) {
+            uint32_t exclusive = 0;
+            if (tile > 0) {
+                atomicExch(&a.tileStatus[tile], pack_status(a.epoch, 1u, blockTotal));
+                int look = (int)tile - 1;
+                while (look >= 0) {
+                    const unsigned long long sv = *((volatile unsigned long long*)&a.tileStatus[look]);
+                    if ((uint32_t)(sv >> 34) != a.epoch) continue;              // not published yet
+                    const uint32_t flag = (uint32_t)(sv >> 32) & 3u;
+                    exclusive += (uint32_t)sv;
+                    if (flag == 2u) break;
+                    look--;
+                }
+            }
+            __threadfence();
+            atomicExch(&a.tileStatus[tile], pack_status(a.epoch, 2u, exclusive + blockTotal));
+            if (tile == numTiles - 1) *a.countOut = exclusive + blockTotal;
+            s_base = exclusive;
+        }
+        __syncthreads();
+        if (survive) {
+            const uint32_t dst = s_base + warpOffset + rankInWarp;
+            float4* op = reinterpret_cast<float4*>(a.stateOut + dst);
+            op[0] = make_float4(st.ox, st.oy, st.oz, st.prevIor);
+            op[1] = make_float4(st.pdx, st.pdy, __uint_as_float(st.pix), 0.0f);
+            op[2] = make_float4(st.tx, st.ty, st.tz, 0.0f);
+            op[3] = make_float4(st.rx, st.ry, st.rz, 0.0f);
+            if (a.outputAovs) { a.aovOut[2 * (size_t)dst] = aov0; a.aovOut[2 * (size_t)dst + 1] = aov1; }
+            if (a.keysOut) a.keysOut[dst] = sortingKey & 0x1FFFFFu;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// FinalDraw/compute.glsl:24-62 over this tile's compact rows.
+__device__ __forceinline__ f3 turbo_colormap(float x) {
+    x = clamp1(x, 0.0f, 1.0f);
+    const float v0 = 1.0f, v1 = x, v2 = x * x, v3 = x * x * x;
+    const float w0 = v2 * v2, w1 = v3 * v2;
+    return mk3((((v0 * 0.13572138f + v1 * 4.61539260f) + v2 * -42.66032258f) + v3 * 132.13108234f) + (w0 * -152.94239396f + w1 * 59.28637943f),
+               (((v0 * 0.09140261f + v1 * 2.19418839f) + v2 * 4.84296658f) + v3 * -14.18503333f) + (w0 * 4.27729857f + w1 * 2.82956604f),
+               (((v0 * 0.10667330f + v1 * 12.64194608f) + v2 * -60.58204836f) + v3 * 110.36276771f) + (w0 * -89.90310912f + w1 * 27.34824973f));
+}
+
+__global__ void __launch_bounds__(IDK_BLOCK) k_accumulate(const float4* __restrict__ radiance, const float4* __restrict__ aovAlbedo,
+                                                          const float4* __restrict__ aovNormal, float4* __restrict__ result,
+                                                          float4* __restrict__ albedo, float4* __restrict__ normal,
+                                                          uint32_t count, uint32_t accumulatedSamples, int debugTraversal, int outputAovs) {
+    const float w = 1.0f / ((float)accumulatedSamples + 1.0f);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const float4 r = radiance[i];
+        f3 nr = mk3(r.x, r.y, r.z);
+        if (debugTraversal) nr = turbo_colormap(r.w / 150.0f);
+        const float4 last = result[i];
+        const f3 o = mix3(mk3(last.x, last.y, last.z), nr, w);
+        result[i] = make_float4(o.x, o.y, o.z, 1.0f);
+        if (outputAovs) {
+            const float4 la = albedo[i], ln = normal[i], a = aovAlbedo[i], n = aovNormal[i];
+            const f3 oa = mix3(mk3(la.x, la.y, la.z), mk3(a.x, a.y, a.z), w);
+            const f3 on = mix3(mk3(ln.x, ln.y, ln.z), mk3(n.x, n.y, n.z), w);
+            albedo[i] = make_float4(oa.x, oa.y, oa.z, 1.0f);
+            normal[i] = make_float4(on.x, on.y, on.z, 1.0f);
+        }
+    }
+}

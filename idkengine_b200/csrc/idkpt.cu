@@ -1,0 +1,666 @@
+// libidkpt: C ABI (include/idkpt.h) over the sm_100a wavefront kernels (idk_kernels.cuh).
+// Host sequencing mirrors PathTracer.Compute(), IDKEngine/Source/Render/PathTracer.cs:214-297, with
+// every GL dispatch replaced by a CUDA launch on one stream and no CPU read-back inside the loop
+// (alive counts stay on the device, like the reference's indirect dispatch).
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include <algorithm>
+
+#include "../../include/idkpt.h"
+#include "idk_kernels.cuh"
+#include "idk_sort.cuh"
+
+#define IDKPT_ABI_VERSION 1u
+
+static thread_local std::string g_createError;
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+};
+
+struct IdkPtCtx {
+    int device = 0;
+    int smCount = 148;
+    cudaStream_t stream = nullptr;
+    std::string lastError;
+
+    // image / tile geometry
+    int width = 0, height = 0;
+    int stripeH = 8, tileIndex = 0, tileCount = 1;
+    std::vector<int> rows;         // owned rows, ascending
+    uint32_t nLocal = 0;           // rows.size() * width
+    uint32_t accumulatedSamples = 0;
+
+    // scene
+    bool haveScene = false;
+    DeviceScene sc = {};
+    IdkPtSceneDesc counts = {};    // element counts only (pointers unused)
+    DevBuf nodes, triRec, blasTris, positions, descs, instances, xforms, meshes, materials, vertices, lights;
+    float sky[3] = {0.0f, 0.0f, 0.0f};
+
+    // wavefront buffers
+    DevBuf state[2], aov[2], hits, hitXform, debugCost, radiance, aovAlbedoFinal, aovNormalFinal, exportRays;
+    DevBuf images[3];
+    DevBuf countsDev;              // uint32 counts[IDKPT_MAX_RAY_DEPTH + 1]
+    DevBuf tickets;                // uint32 tickets[2 * (IDKPT_MAX_RAY_DEPTH + 1)] (traverse, shade)
+    DevBuf tileStatus;             // u64 per tile
+    DevBuf counters;               // TraceCounters
+    DevBuf keys, perm;             // ray sorting
+    IdkSortScratch sortScratch;
+    uint32_t epoch = 0;
+    bool exportEnabled = false;
+
+    // launch configuration
+    int traverseBlocks = 0, traverseBlocksStats = 0, shadeBlocks = 0, traceRaysBlocks = 0;
+    size_t stackBytes = 0;
+
+    std::vector<cudaEvent_t> events;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            char buf_[512];                                                                        \
+            snprintf(buf_, sizeof(buf_), "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            ctx->lastError = buf_;                                                                 \
+            return IDKPT_ERR_CUDA;                                                                 \
+        }                                                                                          \
+    } while (0)
+
+static int fail(IdkPtCtx* ctx, int code, const char* msg) {
+    if (ctx) ctx->lastError = msg; else g_createError = msg;
+    return code;
+}
+
+static cudaError_t ensure(DevBuf& b, size_t bytes) {
+    if (bytes <= b.bytes && b.p) return cudaSuccess;
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+    if (bytes == 0) return cudaSuccess;
+    cudaError_t e = cudaMalloc(&b.p, bytes);
+    if (e == cudaSuccess) b.bytes = bytes;
+    return e;
+}
+
+static void release(DevBuf& b) {
+    if (b.p) cudaFree(b.p);
+    b.p = nullptr;
+    b.bytes = 0;
+}
+
+static int upload(IdkPtCtx* ctx, DevBuf& b, const void* src, size_t bytes) {
+    CK(ensure(b, std::max<size_t>(bytes, 16)));
+    if (bytes) CK(cudaMemcpyAsync(b.p, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return IDKPT_OK;
+}
+
+static void compute_tile_rows(IdkPtCtx* ctx) {
+    ctx->rows.clear();
+    for (int y = 0; y < ctx->height; y++)
+        if (ctx->tileCount <= 1 || ((y / ctx->stripeH) % ctx->tileCount) == ctx->tileIndex) ctx->rows.push_back(y);
+    ctx->nLocal = (uint32_t)(ctx->rows.size() * (size_t)ctx->width);
+}
+
+static int configure_launches(IdkPtCtx* ctx) {
+    const int stackSize = std::max(1, ctx->sc.stackSize);
+    ctx->stackBytes = (size_t)stackSize * IDK_BLOCK * sizeof(uint32_t);
+    if (ctx->stackBytes > 200 * 1024) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "BlasStackSize too large for the shared-memory traversal stack");
+    CK(cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
+    CK(cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
+    CK(cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
+    int n = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
+    ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, IDK_BLOCK, ctx->stackBytes));
+    ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_rays, IDK_BLOCK, ctx->stackBytes));
+    ctx->traceRaysBlocks = std::max(1, n) * ctx->smCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade, IDK_BLOCK, 0));
+    ctx->shadeBlocks = std::max(1, n) * ctx->smCount;
+    return IDKPT_OK;
+}
+
+static int allocate_wavefront(IdkPtCtx* ctx) {
+    const size_t n = std::max<uint32_t>(ctx->nLocal, 1);
+    for (int i = 0; i < 2; i++) {
+        CK(ensure(ctx->state[i], n * sizeof(PathState)));
+        CK(ensure(ctx->aov[i], n * 32));
+    }
+    CK(ensure(ctx->hits, n * 16));
+    CK(ensure(ctx->hitXform, n * 4));
+    CK(ensure(ctx->debugCost, n * 4));
+    CK(ensure(ctx->radiance, n * 16));
+    CK(ensure(ctx->aovAlbedoFinal, n * 16));
+    CK(ensure(ctx->aovNormalFinal, n * 16));
+    for (int i = 0; i < 3; i++) {
+        CK(ensure(ctx->images[i], n * 16));
+        CK(cudaMemsetAsync(ctx->images[i].p, 0, n * 16, ctx->stream));   // Result.Fill(0), PathTracer.cs:305
+    }
+    CK(ensure(ctx->countsDev, (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
+    CK(ensure(ctx->tickets, 2 * (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
+    CK(ensure(ctx->tileStatus, ((n + IDK_BLOCK - 1) / IDK_BLOCK + 1) * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->tileStatus.p, 0, ctx->tileStatus.bytes, ctx->stream));
+    CK(ensure(ctx->counters, sizeof(TraceCounters)));
+    ctx->epoch = 0;
+    return IDKPT_OK;
+}
+
+extern "C" {
+
+IDKPT_API uint32_t idkpt_abi_version(void) { return IDKPT_ABI_VERSION; }
+
+IDKPT_API const char* idkpt_last_error(IdkPtCtx* ctx) { return ctx ? ctx->lastError.c_str() : g_createError.c_str(); }
+
+IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
+    if (!ci || !out) return fail(nullptr, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_create: null argument");
+    *out = nullptr;
+    if (ci->Width <= 0 || ci->Height <= 0 || ci->Width > 4096 * 4 || ci->Height > 4096 * 4)
+        return fail(nullptr, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_create: invalid image size");
+    int stripe = ci->TileStripeHeight > 0 ? ci->TileStripeHeight : 8;
+    int tcount = ci->TileCount > 1 ? ci->TileCount : 1;
+    if (tcount > 1 && (ci->TileIndex < 0 || ci->TileIndex >= tcount))
+        return fail(nullptr, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_create: TileIndex out of range");
+    int deviceCount = 0;
+    cudaError_t e = cudaGetDeviceCount(&deviceCount);
+    if (e != cudaSuccess || deviceCount == 0)
+        return fail(nullptr, IDKPT_ERR_NO_DEVICE, "idkpt_create: no CUDA device (libidkpt has no CPU fallback)");
+    if (ci->Device < 0 || ci->Device >= deviceCount)
+        return fail(nullptr, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_create: device ordinal out of range");
+    if (cudaSetDevice(ci->Device) != cudaSuccess) return fail(nullptr, IDKPT_ERR_CUDA, "idkpt_create: cudaSetDevice failed");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, ci->Device) != cudaSuccess) return fail(nullptr, IDKPT_ERR_CUDA, "idkpt_create: cudaGetDeviceProperties failed");
+    if (prop.major < 10) {
+        char buf[256];
+        snprintf(buf, sizeof(buf), "idkpt_create: device '%s' is sm_%d%d; libidkpt is built for sm_100a only", prop.name, prop.major, prop.minor);
+        return fail(nullptr, IDKPT_ERR_NO_DEVICE, buf);
+    }
+    IdkPtCtx* ctx = new IdkPtCtx();
+    ctx->device = ci->Device;
+    ctx->smCount = prop.multiProcessorCount;
+    ctx->width = ci->Width;
+    ctx->height = ci->Height;
+    ctx->stripeH = stripe;
+    ctx->tileIndex = tcount > 1 ? ci->TileIndex : 0;
+    ctx->tileCount = tcount;
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete ctx;
+        return fail(nullptr, IDKPT_ERR_CUDA, "idkpt_create: cudaStreamCreate failed");
+    }
+    compute_tile_rows(ctx);
+    int rc = allocate_wavefront(ctx);
+    if (rc != IDKPT_OK) {
+        g_createError = ctx->lastError;
+        idkpt_destroy(ctx);
+        return rc;
+    }
+    ctx->sky[0] = ctx->sky[1] = ctx->sky[2] = 0.0f;
+    *out = ctx;
+    return IDKPT_OK;
+}
+
+IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    DevBuf* all[] = {&ctx->nodes, &ctx->triRec, &ctx->blasTris, &ctx->positions, &ctx->descs, &ctx->instances, &ctx->xforms,
+                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->state[0], &ctx->state[1], &ctx->aov[0],
+                     &ctx->aov[1], &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
+                     &ctx->aovNormalFinal, &ctx->exportRays, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
+                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->perm};
+    for (DevBuf* b : all) release(*b);
+    idk_sort_release(ctx->sortScratch);
+    for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
+    if (!ctx || !s) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (!s->BlasNodes || !s->BlasTriangles || !s->BlasDescs || !s->BlasInstances || !s->MeshTransforms || !s->Meshes ||
+        !s->Materials || !s->Vertices || !s->VertexPositions)
+        return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: a required array is null");
+    if (s->LightCount > IDK_GPU_MAX_UBO_LIGHT_COUNT) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: more than 256 lights");
+    if (s->UseTlas) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_scene: UseTlas=1 is not implemented yet (BVH.GpuUseTlas defaults to false)");
+    if (s->BlasTriangleCount >= (1ull << 31) || s->BlasNodeCount >= (1ull << 31)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: scene too large");
+    // validate indices the kernels will chase (a bad host array must not become a device fault)
+    for (uint64_t i = 0; i < s->BlasInstanceCount; i++) {
+        if (s->BlasInstances[i].BlasId >= s->BlasDescCount || s->BlasInstances[i].MeshTransformId >= s->MeshTransformCount)
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: BlasInstance references a missing BLAS or transform");
+    }
+    for (uint64_t i = 0; i < s->BlasDescCount; i++) {
+        const GpuBlasDesc& d = s->BlasDescs[i];
+        if (d.NodeOffset < 0 || d.NodeCount < 4 || (uint64_t)d.NodeOffset + d.NodeCount > s->BlasNodeCount || d.TriangleOffset < 0 ||
+            (uint64_t)d.TriangleOffset + d.TriangleCount > s->BlasTriangleCount)
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuBlasDesc range outside the node/triangle arrays");
+        if (d.RequiredStackSize > s->BlasStackSize)
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: BlasStackSize smaller than a BLAS's RequiredStackSize");
+    }
+    for (uint64_t i = 0; i < s->MeshCount; i++)
+        if (s->Meshes[i].MaterialId < 0 || (uint64_t)s->Meshes[i].MaterialId >= s->MaterialCount)
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuMesh.MaterialId out of range");
+    for (uint64_t i = 0; i < s->MaterialCount; i++) {
+        const GpuMaterial& m = s->Materials[i];
+        if (m.BaseColorTexture || m.MetallicRoughnessTexture || m.NormalTexture || m.EmissiveTexture || m.TransmissionTexture)
+            return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_scene: non-null texture handles are not supported yet (use 0 = 1x1 white)");
+    }
+
+    int rc;
+    if ((rc = upload(ctx, ctx->nodes, s->BlasNodes, s->BlasNodeCount * sizeof(GpuBlasNode)))) return rc;
+    if ((rc = upload(ctx, ctx->blasTris, s->BlasTriangles, s->BlasTriangleCount * sizeof(GpuBlasTriangle)))) return rc;
+    if ((rc = upload(ctx, ctx->positions, s->VertexPositions, s->VertexPositionCount * sizeof(PackedVec3)))) return rc;
+    if ((rc = upload(ctx, ctx->descs, s->BlasDescs, s->BlasDescCount * sizeof(GpuBlasDesc)))) return rc;
+    if ((rc = upload(ctx, ctx->instances, s->BlasInstances, s->BlasInstanceCount * sizeof(GpuBlasInstance)))) return rc;
+    if ((rc = upload(ctx, ctx->xforms, s->MeshTransforms, s->MeshTransformCount * sizeof(GpuMeshTransform)))) return rc;
+    if ((rc = upload(ctx, ctx->meshes, s->Meshes, s->MeshCount * sizeof(GpuMesh)))) return rc;
+    if ((rc = upload(ctx, ctx->materials, s->Materials, s->MaterialCount * sizeof(GpuMaterial)))) return rc;
+    if ((rc = upload(ctx, ctx->vertices, s->Vertices, s->VertexCount * sizeof(GpuVertex)))) return rc;
+    if ((rc = upload(ctx, ctx->lights, s->Lights, s->LightCount * sizeof(GpuLight)))) return rc;
+    CK(ensure(ctx->triRec, std::max<size_t>(s->BlasTriangleCount, 1) * 48));
+
+    // triangle vertex ids must index the position / vertex arrays
+    // (checked on the host copy: cheap relative to the BVH build that produced it)
+    for (uint64_t i = 0; i < s->BlasTriangleCount; i++) {
+        const GpuBlasTriangle& t = s->BlasTriangles[i];
+        const uint64_t lim = std::min(s->VertexPositionCount, s->VertexCount);
+        if ((uint64_t)(uint32_t)t.X >= lim || (uint64_t)(uint32_t)t.Y >= lim || (uint64_t)(uint32_t)t.Z >= lim || t.MeshId < 0 || (uint64_t)t.MeshId >= s->MeshCount)
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuBlasTriangle index out of range");
+    }
+    if (s->BlasTriangleCount) {
+        const uint32_t n = (uint32_t)s->BlasTriangleCount;
+        k_prepare_triangles<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const int4*)ctx->blasTris.p, (const float*)ctx->positions.p, (float4*)ctx->triRec.p, n);
+        CK(cudaGetLastError());
+    }
+
+    DeviceScene& sc = ctx->sc;
+    sc.nodes = (const float4*)ctx->nodes.p;
+    sc.triRec = (const float4*)ctx->triRec.p;
+    sc.blasTris = (const int4*)ctx->blasTris.p;
+    sc.descs = (const GpuBlasDesc*)ctx->descs.p;
+    sc.instances = (const GpuBlasInstance*)ctx->instances.p;
+    sc.xforms = (const float4*)ctx->xforms.p;
+    sc.meshes = (const GpuMesh*)ctx->meshes.p;
+    sc.materials = (const GpuMaterial*)ctx->materials.p;
+    sc.vertices = (const uint4*)ctx->vertices.p;
+    sc.lights = (const GpuLight*)ctx->lights.p;
+    sc.instanceCount = (uint32_t)s->BlasInstanceCount;
+    sc.lightCount = (uint32_t)s->LightCount;
+    sc.skyR = ctx->sky[0]; sc.skyG = ctx->sky[1]; sc.skyB = ctx->sky[2];
+    sc.stackSize = std::max(1, s->BlasStackSize);
+    ctx->counts = *s;
+    if ((rc = configure_launches(ctx))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->haveScene = true;
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t first, uint64_t count, const void* data) {
+    if (!ctx || !data) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: null argument");
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_update_range: no scene");
+    CK(cudaSetDevice(ctx->device));
+    DevBuf* b = nullptr;
+    size_t elem = 0;
+    uint64_t limit = 0;
+    switch (which) {
+        case IDKPT_ARRAY_MESH_TRANSFORMS: b = &ctx->xforms; elem = sizeof(GpuMeshTransform); limit = ctx->counts.MeshTransformCount; break;
+        case IDKPT_ARRAY_MESHES: b = &ctx->meshes; elem = sizeof(GpuMesh); limit = ctx->counts.MeshCount; break;
+        case IDKPT_ARRAY_MATERIALS: b = &ctx->materials; elem = sizeof(GpuMaterial); limit = ctx->counts.MaterialCount; break;
+        case IDKPT_ARRAY_LIGHTS: b = &ctx->lights; elem = sizeof(GpuLight); limit = ctx->counts.LightCount; break;
+        default: return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: unknown array id");
+    }
+    if (first + count > limit) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: range outside the array");
+    if (which == IDKPT_ARRAY_MESHES) {
+        const GpuMesh* m = (const GpuMesh*)data;
+        for (uint64_t i = 0; i < count; i++)
+            if (m[i].MaterialId < 0 || (uint64_t)m[i].MaterialId >= ctx->counts.MaterialCount)
+                return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: GpuMesh.MaterialId out of range");
+    }
+    CK(cudaMemcpyAsync((char*)b->p + first * elem, data, count * elem, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_set_sky(IdkPtCtx* ctx, const IdkPtSkyDesc* sky) {
+    if (!ctx || !sky) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_sky: null argument");
+    if (sky->FaceSize != 0) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_sky: cubemap faces are not implemented yet (constant colour only)");
+    for (int i = 0; i < 3; i++) ctx->sky[i] = sky->Color[i];
+    ctx->sc.skyR = ctx->sky[0]; ctx->sc.skyG = ctx->sky[1]; ctx->sc.skyB = ctx->sky[2];
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    if (width <= 0 || height <= 0 || width > 16384 || height > 16384) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_resize: invalid size");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->width = width;
+    ctx->height = height;
+    compute_tile_rows(ctx);
+    int rc = allocate_wavefront(ctx);
+    if (rc) return rc;
+    release(ctx->exportRays);
+    release(ctx->keys);
+    release(ctx->perm);
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_reset_accumulation(IdkPtCtx* ctx) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+IDKPT_API uint32_t idkpt_accumulated_samples(IdkPtCtx* ctx) { return ctx ? ctx->accumulatedSamples : 0; }
+
+IDKPT_API int idkpt_set_accumulated_samples(IdkPtCtx* ctx, uint32_t n) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    ctx->accumulatedSamples = n;
+    return IDKPT_OK;
+}
+
+struct EventPool {
+    IdkPtCtx* ctx;
+    size_t used = 0;
+    struct Span { size_t a, b; int cat; };
+    std::vector<Span> spans;
+    bool enabled;
+    cudaEvent_t get() {
+        if (used == ctx->events.size()) {
+            cudaEvent_t e;
+            cudaEventCreate(&e);
+            ctx->events.push_back(e);
+        }
+        return ctx->events[used++];
+    }
+    size_t begin() {
+        if (!enabled) return 0;
+        size_t i = used;
+        cudaEventRecord(get(), ctx->stream);
+        return i;
+    }
+    void end(size_t a, int cat) {
+        if (!enabled) return;
+        size_t i = used;
+        cudaEventRecord(get(), ctx->stream);
+        spans.push_back({a, i, cat});
+    }
+};
+
+IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const IdkPtSettings* st, IdkPtStats* stats) {
+    if (!ctx || !frame || !st) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_compute: null argument");
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_compute: idkpt_set_scene has not been called");
+    if (st->RayDepth < 1 || st->RayDepth > IDKPT_MAX_RAY_DEPTH) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_compute: RayDepth out of range");
+    if (st->SamplesPerPixel < 1) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_compute: SamplesPerPixel must be >= 1");
+    CK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    const uint32_t n = ctx->nLocal;
+    if (n == 0) { ctx->accumulatedSamples += st->SamplesPerPixel; return IDKPT_OK; }
+
+    const bool wantStats = st->CollectStats != 0 || st->Gpu.DoDebugBVHTraversal != 0;
+    const bool sorting = st->DoRaySorting != 0;
+    const bool aovs = st->OutputAOVs != 0;
+    if (sorting) {
+        CK(ensure(ctx->keys, (size_t)n * 4));
+        CK(ensure(ctx->perm, (size_t)n * 4));
+        int rc = idk_sort_prepare(ctx->sortScratch, n);
+        if (rc) return fail(ctx, IDKPT_ERR_OUT_OF_MEMORY, "idkpt_compute: sort scratch allocation failed");
+    }
+    if (ctx->exportEnabled) CK(ensure(ctx->exportRays, (size_t)n * sizeof(GpuWavefrontRay)));
+
+    FrameParams f;
+    memcpy(f.invProj, frame->InvProjection, sizeof(f.invProj));
+    memcpy(f.invView, frame->InvView, sizeof(f.invView));
+    memcpy(f.viewPos, frame->ViewPos, sizeof(f.viewPos));
+    f.focalLength = st->Gpu.FocalLength;
+    f.lenseRadius = st->Gpu.LenseRadius;
+    f.width = ctx->width; f.height = ctx->height;
+    f.stripeH = ctx->stripeH; f.tileIndex = ctx->tileIndex; f.tileCount = ctx->tileCount;
+    f.doDebugTraversal = st->Gpu.DoDebugBVHTraversal;
+    f.doTraceLights = st->Gpu.DoTraceLights;
+    f.doRussianRoulette = st->Gpu.DoRussianRoulette;
+
+    EventPool ev{ctx, 0, {}, stats != nullptr};
+    const size_t evTotal = ev.begin();
+    uint32_t* counts = (uint32_t*)ctx->countsDev.p;
+    uint32_t* tickets = (uint32_t*)ctx->tickets.p;
+    uint32_t launches = 0, traverseLaunches = 0;
+    std::vector<uint32_t> hostCounts((size_t)st->SamplesPerPixel * (IDKPT_MAX_RAY_DEPTH + 1), 0);
+    DevBuf countLog;   // per-sample copy of counts for the stats (device-side, read once at the end)
+    if (stats) CK(ensure(countLog, hostCounts.size() * sizeof(uint32_t)));
+    if (wantStats) CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(TraceCounters), ctx->stream));
+
+    const dim3 rgGrid((ctx->width + 7) / 8, (ctx->height + 7) / 8), rgBlock(8, 8);
+    const int accBlocks = std::min<int>((int)((n + IDK_BLOCK - 1) / IDK_BLOCK), ctx->smCount * 8);
+
+    for (int s = 0; s < st->SamplesPerPixel; s++) {
+        f.accumulatedSamples = ctx->accumulatedSamples;
+        CK(cudaMemsetAsync(counts, 0, ctx->countsDev.bytes, ctx->stream));
+        CK(cudaMemsetAsync(tickets, 0, ctx->tickets.bytes, ctx->stream));
+        // counts[0] = n (every pixel of the tile traces a primary ray)
+        CK(cudaMemcpyAsync(counts, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+
+        size_t e0 = ev.begin();
+        k_raygen<<<rgGrid, rgBlock, 0, ctx->stream>>>(f, (PathState*)ctx->state[0].p);
+        ev.end(e0, 3);
+        launches++;
+
+        int cur = 0;
+        for (int j = 0; j < st->RayDepth; j++) {
+            const bool first = j == 0;
+            const bool last = j == st->RayDepth - 1;
+            const uint32_t* perm = nullptr;
+            if (sorting && j > 1) {
+                // PathTracer.RaySorting(), PathTracer.cs:273-297: stable sort of the alive list by cached key
+                e0 = ev.begin();
+                int nl = idk_sort_by_key(ctx->sortScratch, (const uint32_t*)ctx->keys.p, (uint32_t*)ctx->perm.p, counts + j, n, ctx->smCount, ctx->stream);
+                ev.end(e0, 2);
+                if (nl < 0) return fail(ctx, IDKPT_ERR_CUDA, "idkpt_compute: sort launch failed");
+                launches += (uint32_t)nl;
+                perm = (const uint32_t*)ctx->perm.p;
+            }
+
+            TraverseArgs ta;
+            ta.sc = ctx->sc;
+            ta.state = (const PathState*)ctx->state[cur].p;
+            ta.perm = perm;
+            ta.count = counts + j;
+            ta.ticket = tickets + 2 * j;
+            ta.hits = (HitRec*)ctx->hits.p;
+            ta.hitXform = (uint32_t*)ctx->hitXform.p;
+            ta.debugCost = (float*)ctx->debugCost.p;
+            ta.counters = (TraceCounters*)ctx->counters.p;
+            ta.traceLights = st->Gpu.DoTraceLights;
+            e0 = ev.begin();
+            if (wantStats) k_traverse<true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
+            else k_traverse<false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
+            ev.end(e0, 0);
+            launches++;
+            traverseLaunches++;
+
+            ShadeArgs sa;
+            sa.sc = ctx->sc;
+            sa.f = f;
+            sa.stateIn = (const PathState*)ctx->state[cur].p;
+            sa.stateOut = (PathState*)ctx->state[cur ^ 1].p;
+            sa.aovIn = (const float4*)ctx->aov[cur].p;
+            sa.aovOut = (float4*)ctx->aov[cur ^ 1].p;
+            sa.perm = perm;
+            sa.hits = (const HitRec*)ctx->hits.p;
+            sa.hitXform = (const uint32_t*)ctx->hitXform.p;
+            sa.debugCost = (const float*)ctx->debugCost.p;
+            sa.count = counts + j;
+            sa.countOut = counts + j + 1;
+            sa.ticket = tickets + 2 * j + 1;
+            sa.tileStatus = (unsigned long long*)ctx->tileStatus.p;
+            sa.epoch = ++ctx->epoch;
+            sa.keysOut = sorting ? (uint32_t*)ctx->keys.p : nullptr;
+            sa.radiance = (float4*)ctx->radiance.p;
+            sa.aovAlbedoFinal = (float4*)ctx->aovAlbedoFinal.p;
+            sa.aovNormalFinal = (float4*)ctx->aovNormalFinal.p;
+            sa.exportRays = ctx->exportEnabled ? (GpuWavefrontRay*)ctx->exportRays.p : nullptr;
+            sa.firstHit = first ? 1 : 0;
+            sa.lastBounce = last ? 1 : 0;
+            sa.outputAovs = aovs ? 1 : 0;
+            e0 = ev.begin();
+            k_shade<<<ctx->shadeBlocks, IDK_BLOCK, 0, ctx->stream>>>(sa);
+            ev.end(e0, 1);
+            launches++;
+            cur ^= 1;
+        }
+
+        e0 = ev.begin();
+        k_accumulate<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ctx->radiance.p, (const float4*)ctx->aovAlbedoFinal.p,
+                                                               (const float4*)ctx->aovNormalFinal.p, (float4*)ctx->images[0].p,
+                                                               (float4*)ctx->images[1].p, (float4*)ctx->images[2].p, n,
+                                                               ctx->accumulatedSamples, st->Gpu.DoDebugBVHTraversal, aovs ? 1 : 0);
+        ev.end(e0, 3);
+        launches++;
+        if (stats) CK(cudaMemcpyAsync((uint32_t*)countLog.p + (size_t)s * (IDKPT_MAX_RAY_DEPTH + 1), counts,
+                                      (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
+        ctx->accumulatedSamples++;   // PathTracer.cs:269
+    }
+    ev.end(evTotal, 4);
+    CK(cudaGetLastError());
+    cudaError_t se = cudaStreamSynchronize(ctx->stream);
+    if (se != cudaSuccess) {
+        release(countLog);
+        ctx->lastError = std::string("idkpt_compute: kernel execution failed: ") + cudaGetErrorString(se);
+        return IDKPT_ERR_CUDA;
+    }
+
+    if (stats) {
+        CK(cudaMemcpy(hostCounts.data(), countLog.p, hostCounts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+        for (int s = 0; s < st->SamplesPerPixel; s++)
+            for (int j = 0; j < st->RayDepth; j++) {
+                const uint64_t c = hostCounts[(size_t)s * (IDKPT_MAX_RAY_DEPTH + 1) + j];
+                stats->BounceRays[j] += c;
+                stats->Rays += c;
+            }
+        if (wantStats) {
+            TraceCounters tc;
+            CK(cudaMemcpy(&tc, ctx->counters.p, sizeof(tc), cudaMemcpyDeviceToHost));
+            stats->NodePairFetches = tc.steps;
+            stats->TriangleTests = tc.tris;
+            stats->InstanceVisits = tc.instances;
+            stats->Hits = tc.hits;
+        }
+        for (const EventPool::Span& sp : ev.spans) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, ctx->events[sp.a], ctx->events[sp.b]);
+            switch (sp.cat) {
+                case 0: stats->TraverseMs += ms; break;
+                case 1: stats->ShadeMs += ms; break;
+                case 2: stats->SortMs += ms; break;
+                case 3: stats->OtherMs += ms; break;
+                default: stats->TotalMs = ms; break;
+            }
+        }
+        stats->KernelLaunches = launches;
+        stats->TraverseLaunches = traverseLaunches;
+    }
+    release(countLog);
+    return IDKPT_OK;
+}
+
+static int image_copy(IdkPtCtx* ctx, IdkPtImage which, void* host, uint64_t bytes, bool toHost) {
+    if (!ctx || !host) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt image copy: null argument");
+    if ((int)which < 0 || (int)which > 2) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt image copy: unknown image");
+    if (bytes < (uint64_t)ctx->width * ctx->height * 16) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt image copy: buffer smaller than width*height*16");
+    CK(cudaSetDevice(ctx->device));
+    const size_t rowBytes = (size_t)ctx->width * 16;
+    // owned rows are stored compactly; copy stripe by stripe into the full-image layout
+    size_t i = 0;
+    while (i < ctx->rows.size()) {
+        size_t j = i;
+        while (j + 1 < ctx->rows.size() && ctx->rows[j + 1] == ctx->rows[j] + 1) j++;
+        char* h = (char*)host + (size_t)ctx->rows[i] * rowBytes;
+        char* d = (char*)ctx->images[which].p + i * rowBytes;
+        if (toHost) CK(cudaMemcpyAsync(h, d, (j - i + 1) * rowBytes, cudaMemcpyDeviceToHost, ctx->stream));
+        else CK(cudaMemcpyAsync(d, h, (j - i + 1) * rowBytes, cudaMemcpyHostToDevice, ctx->stream));
+        i = j + 1;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_read_result(IdkPtCtx* ctx, IdkPtImage which, void* dst, uint64_t bytes) { return image_copy(ctx, which, dst, bytes, true); }
+IDKPT_API int idkpt_write_result(IdkPtCtx* ctx, IdkPtImage which, const void* src, uint64_t bytes) { return image_copy(ctx, which, (void*)src, bytes, false); }
+
+IDKPT_API int idkpt_result_device_ptr(IdkPtCtx* ctx, IdkPtImage which, void** devPtr, uint64_t* bytes) {
+    if (!ctx || !devPtr || (int)which < 0 || (int)which > 2) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_result_device_ptr: invalid argument");
+    *devPtr = ctx->images[which].p;
+    if (bytes) *bytes = (uint64_t)ctx->nLocal * 16;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_tile_rows(IdkPtCtx* ctx, int32_t* rowCount, int32_t* rowsOut, int32_t capacity) {
+    if (!ctx || !rowCount) return IDKPT_ERR_INVALID_ARGUMENT;
+    *rowCount = (int32_t)ctx->rows.size();
+    if (rowsOut) for (int i = 0; i < capacity && i < (int)ctx->rows.size(); i++) rowsOut[i] = ctx->rows[i];
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_read_wavefront_rays(IdkPtCtx* ctx, GpuWavefrontRay* dst, uint64_t count) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    if (!dst) {   // dst == NULL arms the export for subsequent idkpt_compute calls (debug / parity feature)
+        ctx->exportEnabled = count != 0;
+        return IDKPT_OK;
+    }
+    if (!ctx->exportEnabled || !ctx->exportRays.p) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_wavefront_rays: arm the export first (dst = NULL, count = 1) and call idkpt_compute");
+    if (count < (uint64_t)ctx->width * ctx->height) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_wavefront_rays: buffer smaller than width*height");
+    CK(cudaSetDevice(ctx->device));
+    const size_t rowBytes = (size_t)ctx->width * sizeof(GpuWavefrontRay);
+    for (size_t i = 0; i < ctx->rows.size(); i++)
+        CK(cudaMemcpyAsync((char*)dst + (size_t)ctx->rows[i] * rowBytes, (char*)ctx->exportRays.p + i * rowBytes, rowBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_trace_rays(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, int32_t traceLights, IdkPtHit* hitsOut, float* kernelMs) {
+    if (!ctx || (!rays && count) || (!hitsOut && count)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_trace_rays: null argument");
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_trace_rays: no scene");
+    if (count >= (1ull << 31)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_trace_rays: too many rays");
+    if (kernelMs) *kernelMs = 0.0f;
+    if (count == 0) return IDKPT_OK;
+    CK(cudaSetDevice(ctx->device));
+    DevBuf dr, dh, dt;
+    int rc = IDKPT_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        if (ensure(dr, count * 32) != cudaSuccess || ensure(dh, count * 32) != cudaSuccess || ensure(dt, 16) != cudaSuccess) { rc = fail(ctx, IDKPT_ERR_OUT_OF_MEMORY, "idkpt_trace_rays: device allocation failed"); break; }
+        cudaMemcpyAsync(dr.p, rays, count * 32, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemsetAsync(dt.p, 0, 16, ctx->stream);
+        TraceRaysArgs a;
+        a.sc = ctx->sc;
+        a.rays = (const float4*)dr.p;
+        a.hits = (uint4*)dh.p;
+        a.count = (uint32_t)count;
+        a.ticket = (uint32_t*)dt.p;
+        a.traceLights = traceLights;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+        k_trace_rays<<<ctx->traceRaysBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(a);
+        cudaEventRecord(e1, ctx->stream);
+        cudaMemcpyAsync(hitsOut, dh.p, count * 32, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_trace_rays: ") + cudaGetErrorString(e); rc = IDKPT_ERR_CUDA; break; }
+        if (kernelMs) cudaEventElapsedTime(kernelMs, e0, e1);
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    release(dr); release(dh); release(dt);
+    return rc;
+}
+
+} // extern "C"

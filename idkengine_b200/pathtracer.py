@@ -1,0 +1,190 @@
+"""PathTracer: host-side mirror of IDKEngine.Render.PathTracer (SRC/Render/PathTracer.cs:10-346) whose body is the
+libidkpt C ABI instead of GL dispatches -- the Python twin of the C# PathTracerNative class in INTEGRATION.md.
+
+Same public members and meaning: ctor(width, height, settings), Compute(), SetSize(), ResetAccumulation(),
+properties SamplesPerPixel, RayDepth, AccumulatedSamples, FocalLength, LenseRadius, DoDebugBVHTraversal,
+DoTraceLights, DoRussianRoulette, DoRaySorting, OutputAOVs, images Result / AlbedoTexture / NormalTexture.
+Setters reset the accumulation exactly where the C# setters do (PathTracer.cs:16-97).
+Scene data the reference binds globally (SSBO/UBO slots) is handed over with SetScene()/SetSky()/SetFrame().
+"""
+import ctypes
+
+import numpy as np
+
+from . import capi
+from . import gpu_types as gt
+
+
+class IdkPtError(RuntimeError):
+    pass
+
+
+class PathTracer:
+    def __init__(self, width, height, settings=None, device=0, tile=(8, 0, 1), lib_path=None):
+        self._lib = capi.load(lib_path)
+        self._ctx = ctypes.c_void_p()
+        self._settings = settings or capi.default_settings()
+        ci = capi.IdkPtCreateInfo(device, width, height, tile[0], tile[1], tile[2], 0)
+        rc = self._lib.idkpt_create(ctypes.byref(ci), ctypes.byref(self._ctx))
+        if rc != 0:
+            msg = self._lib.idkpt_last_error(None)
+            raise IdkPtError(f"idkpt_create failed ({rc}): {msg.decode() if msg else ''}")
+        self.width, self.height = width, height
+        self.tile = tile
+        self._frame = None
+        self._keep = None
+        self.last_stats = None
+        self._export = False
+
+    # ------------------------------------------------------------------ plumbing
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self._lib.idkpt_last_error(self._ctx)
+            raise IdkPtError(f"{what} failed ({rc}): {msg.decode() if msg else ''}")
+
+    def Dispose(self):
+        if self._ctx:
+            self._lib.idkpt_destroy(self._ctx)
+            self._ctx = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.Dispose()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.Dispose()
+
+    # ------------------------------------------------------------------ scene hand-over
+    def SetScene(self, scene):
+        d, keep = capi.scene_desc(scene)
+        self._check(self._lib.idkpt_set_scene(self._ctx, ctypes.byref(d)), "idkpt_set_scene")
+
+    def UpdateRange(self, which, first, data):
+        data = np.ascontiguousarray(data)
+        self._check(self._lib.idkpt_update_range(self._ctx, which, first, len(data), data.ctypes.data), "idkpt_update_range")
+
+    def SetSky(self, color):
+        s = capi.sky_desc(color)
+        self._check(self._lib.idkpt_set_sky(self._ctx, ctypes.byref(s)), "idkpt_set_sky")
+
+    def SetFrame(self, per_frame_data):
+        """GpuPerFrameData (UBO 1). A changed camera resets the accumulation like Application.OnRender does
+        (SRC/Application.cs:209-213)."""
+        pf = np.ascontiguousarray(per_frame_data)
+        assert pf.dtype == gt.GpuPerFrameData
+        if self._frame is not None and pf.tobytes() != self._frame.tobytes():
+            self.ResetAccumulation()
+        self._frame = pf.copy()
+
+    # ------------------------------------------------------------------ PathTracer surface
+    def Compute(self, want_stats=True):
+        if self._frame is None:
+            raise IdkPtError("SetFrame() has not been called")
+        stats = capi.IdkPtStats() if want_stats else None
+        rc = self._lib.idkpt_compute(self._ctx, self._frame.ctypes.data, ctypes.byref(self._settings),
+                                     ctypes.byref(stats) if want_stats else None)
+        self._check(rc, "idkpt_compute")
+        self.last_stats = stats
+        return stats
+
+    def SetSize(self, width, height):
+        self._check(self._lib.idkpt_resize(self._ctx, width, height), "idkpt_resize")
+        self.width, self.height = width, height
+
+    def ResetAccumulation(self):
+        self._check(self._lib.idkpt_reset_accumulation(self._ctx), "idkpt_reset_accumulation")
+
+    @property
+    def AccumulatedSamples(self):
+        return int(self._lib.idkpt_accumulated_samples(self._ctx))
+
+    def _read(self, which):
+        img = np.zeros((self.height, self.width, 4), np.float32)
+        self._check(self._lib.idkpt_read_result(self._ctx, which, img.ctypes.data, img.nbytes), "idkpt_read_result")
+        return img
+
+    @property
+    def Result(self):
+        return self._read(capi.IDKPT_IMAGE_RESULT)
+
+    @property
+    def AlbedoTexture(self):
+        return self._read(capi.IDKPT_IMAGE_ALBEDO)
+
+    @property
+    def NormalTexture(self):
+        return self._read(capi.IDKPT_IMAGE_NORMAL)
+
+    def WriteResult(self, img, which=capi.IDKPT_IMAGE_RESULT, accumulated=None):
+        img = np.ascontiguousarray(img, np.float32)
+        self._check(self._lib.idkpt_write_result(self._ctx, which, img.ctypes.data, img.nbytes), "idkpt_write_result")
+        if accumulated is not None:
+            self._check(self._lib.idkpt_set_accumulated_samples(self._ctx, accumulated), "idkpt_set_accumulated_samples")
+
+    def ResultDevicePtr(self, which=capi.IDKPT_IMAGE_RESULT):
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self._lib.idkpt_result_device_ptr(self._ctx, which, ctypes.byref(p), ctypes.byref(n)), "idkpt_result_device_ptr")
+        return p.value, n.value
+
+    def TileRows(self):
+        n = ctypes.c_int32()
+        self._lib.idkpt_tile_rows(self._ctx, ctypes.byref(n), None, 0)
+        rows = np.zeros(n.value, np.int32)
+        self._lib.idkpt_tile_rows(self._ctx, ctypes.byref(n), rows.ctypes.data, n.value)
+        return rows
+
+    def EnableWavefrontExport(self, on=True):
+        self._export = on
+        self._check(self._lib.idkpt_read_wavefront_rays(self._ctx, None, 1 if on else 0), "idkpt_read_wavefront_rays")
+
+    def ReadWavefrontRays(self):
+        rays = np.zeros(self.width * self.height, gt.GpuWavefrontRay)
+        self._check(self._lib.idkpt_read_wavefront_rays(self._ctx, rays.ctypes.data, len(rays)), "idkpt_read_wavefront_rays")
+        return rays
+
+    def TraceRays(self, rays, trace_lights=False):
+        """Stand-alone closest-hit batch (GPU analogue of BVH.Intersect, SRC/Bvh/BVH.cs:162-193)."""
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == gt.IdkPtRay
+        hits = np.zeros(len(rays), gt.IdkPtHit)
+        ms = ctypes.c_float()
+        self._check(self._lib.idkpt_trace_rays(self._ctx, rays.ctypes.data, len(rays), int(trace_lights),
+                                               hits.ctypes.data, ctypes.byref(ms)), "idkpt_trace_rays")
+        return hits, ms.value
+
+    # ---- properties with the reference's reset-on-set behaviour
+    def _reset_prop(name, sub=None):  # noqa: N805
+        def get(self):
+            return getattr(self._settings.Gpu if sub else self._settings, name)
+
+        def set_(self, v):
+            setattr(self._settings.Gpu if sub else self._settings, name, v)
+            self.ResetAccumulation()
+        return property(get, set_)
+
+    def _plain_prop(name):  # noqa: N805
+        def get(self):
+            return getattr(self._settings, name)
+
+        def set_(self, v):
+            setattr(self._settings, name, v)
+        return property(get, set_)
+
+    RayDepth = _reset_prop("RayDepth")                          # PathTracer.cs:16-25
+    FocalLength = _reset_prop("FocalLength", True)              # :39-48
+    LenseRadius = _reset_prop("LenseRadius", True)              # :50-59
+    DoDebugBVHTraversal = _reset_prop("DoDebugBVHTraversal", True)  # :61-71
+    DoTraceLights = _reset_prop("DoTraceLights", True)          # :73-84
+    DoRussianRoulette = _reset_prop("DoRussianRoulette", True)  # :86-97
+    SamplesPerPixel = _plain_prop("SamplesPerPixel")            # :12
+    DoRaySorting = _plain_prop("DoRaySorting")                  # :101-111
+    OutputAOVs = _plain_prop("OutputAOVs")                      # :113-125
+    CollectStats = _plain_prop("CollectStats")
+
+    def GetGpuSettings(self):
+        return self._settings.Gpu
