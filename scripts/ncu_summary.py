@@ -1,0 +1,71 @@
+#!/usr/bin/env python
+"""Turn ncu outputs brought back in gpurun_out/ into the small text summaries committed under profiles/.
+
+  python scripts/ncu_summary.py launches gpurun_out/launches.csv        > profiles/<name>_launches.txt
+  python scripts/ncu_summary.py full     gpurun_out/prof.ncu-rep        > profiles/<name>_full.txt
+"""
+import csv
+import subprocess
+import sys
+from collections import defaultdict
+
+METRICS = [
+    "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+    "lts__t_sector_hit_rate.pct", "l1tex__t_sector_hit_rate.pct", "lts__throughput.avg.pct_of_peak_sustained_elapsed",
+    "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+    "sm__warps_active.avg.pct_of_peak_sustained_active", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+    "smsp__thread_inst_executed_per_inst_executed.ratio", "smsp__inst_executed.sum", "launch__registers_per_thread",
+    "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__grid_size", "launch__block_size",
+    "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.max", "lts__t_bytes.sum", "l1tex__t_bytes.sum",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_branch_resolving_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_wait_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_no_instruction_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_not_selected_per_issue_active.ratio",
+]
+
+
+def launches(path):
+    rows = [r for r in csv.reader(open(path)) if len(r) > 10]
+    hdr = rows[0]
+    ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
+    seq = [(r[ki].split("(")[0].replace("void ", ""), float(r[vi].replace(",", ""))) for r in rows[1:] if r[mi] == "gpu__time_duration.sum"]
+    print(f"# {path}: {len(seq)} launches (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare SHARES)")
+    starts = [i for i, (k, _) in enumerate(seq) if k.startswith("k_raygen") or k.startswith("k_vx_clear")]
+    if len(starts) >= 2:
+        a, b = starts[-2], starts[-1]
+        print(f"# one full step (launches {a}..{b - 1}):")
+        tot = defaultdict(float)
+        for k, v in seq[a:b]:
+            print(f"{k:44s} {v / 1000:10.1f} us")
+            tot[k] += v
+        T = sum(tot.values())
+        print("# shares of the step:")
+        for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
+            print(f"{k:44s} {v / 1000:10.1f} us {v / T * 100:6.1f} %")
+    tot = defaultdict(lambda: [0, 0.0])
+    for k, v in seq:
+        tot[k][0] += 1
+        tot[k][1] += v
+    print("# all launches:")
+    for k, (n, v) in sorted(tot.items(), key=lambda kv: -kv[1][1]):
+        print(f"{k:44s} n={n:4d} total {v / 1000:10.1f} us  avg {v / n / 1000:9.1f} us")
+
+
+def full(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    print(f"# {path}: ncu --set full --clock-control none --import-source on; {len(rows) - 2} launch(es)")
+    for name in ["Kernel Name"] + METRICS:
+        if name in hdr:
+            i = hdr.index(name)
+            print(f"{name:84s} [{units[i]:12s}] " + "  ".join(r[i] for r in rows[2:]))
+
+
+if __name__ == "__main__":
+    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
