@@ -199,6 +199,7 @@ def run_ours(args, rank, world, local_rank):
     ptr, nbytes = pt.ResultDevicePtr()
     local = torch.as_tensor(multigpu.DeviceArray(ptr, (len(rows), args.width, 4)), device=dev)
     pinned = torch.empty((args.height, args.width, 4), dtype=torch.float32).pin_memory()
+    gatherer = multigpu.TileGatherer(args.height, args.width, 4, STRIPE, world, dev) if world > 1 else None
 
     def barrier():
         if world > 1:
@@ -207,7 +208,7 @@ def run_ours(args, rank, world, local_rank):
 
     def step(e2e):
         st = pt.Compute()
-        full = multigpu.all_gather_tiles(local, args.height, STRIPE, world) if world > 1 else local
+        full = gatherer.gather(local) if world > 1 else local
         if e2e and rank == 0:
             pinned.copy_(full.view(args.height, args.width, 4) if world == 1 else full, non_blocking=False)
         return st
@@ -241,7 +242,7 @@ def run_ours(args, rank, world, local_rank):
         rays += st.Rays; launches += st.KernelLaunches; trav_launches += st.TraverseLaunches
         if world > 1:
             ev0.record()
-            multigpu.all_gather_tiles(local, args.height, STRIPE, world)
+            gatherer.gather(local)
             ev1.record()
             ev1.synchronize()
             gather_ms += ev0.elapsed_time(ev1)

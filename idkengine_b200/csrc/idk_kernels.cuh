@@ -49,6 +49,12 @@ struct HitRec { float bx, by, t; uint32_t tri; };   // 16 bytes, + uint32 transf
 struct TraceCounters { unsigned long long steps, tris, instances, hits; };
 
 // ------------------------------------------------------------------------------------------------
+// Per sample: zero the alive counts and the work tickets, counts[0] = number of primary rays.
+__global__ void k_init_sample(uint32_t* counts, int nCounts, uint32_t* tickets, int nTickets, uint32_t primaryRays) {
+    for (int i = threadIdx.x; i < nCounts; i += blockDim.x) counts[i] = i == 0 ? primaryRays : 0u;
+    for (int i = threadIdx.x; i < nTickets; i += blockDim.x) tickets[i] = 0u;
+}
+
 __global__ void k_prepare_triangles(const int4* __restrict__ tris, const float* __restrict__ positions,
                                     float4* __restrict__ triRec, uint32_t count) {
     uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -203,6 +209,199 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse(TraverseArgs a) {
             if (STATS) {
                 a.debugCost[gid] = cost;
                 if (hit.tri != ~0u) H++;
+            }
+        }
+    }
+    if (STATS) {
+        for (int off = 16; off > 0; off >>= 1) {
+            S += __shfl_down_sync(0xffffffffu, S, off);
+            T += __shfl_down_sync(0xffffffffu, T, off);
+            I += __shfl_down_sync(0xffffffffu, I, off);
+            H += __shfl_down_sync(0xffffffffu, H, off);
+        }
+        if (lane == 0) {
+            atomicAdd(&a.counters->steps, (unsigned long long)S);
+            atomicAdd(&a.counters->tris, (unsigned long long)T);
+            atomicAdd(&a.counters->instances, (unsigned long long)I);
+            atomicAdd(&a.counters->hits, (unsigned long long)H);
+        }
+    }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// k_traverse2: the production traversal kernel. Same per-ray operation sequence as trace_closest (hence the same
+// bits and the same S/T/I counters), but the warp is scheduled as a small state machine so that divergent work is
+// batched instead of serialised:
+//   SETUP  lanes whose ray is finished write their hit, claim a new slot (one atomicAdd per warp for all needy
+//          lanes -- persistent threads with lane refill) and set up the next BLAS instance (local ray, root test);
+//   BOX    lanes test one sibling pair, decide descend / pop (independent of the leaf results, exactly as in the
+//          reference where hitLeft/hitRight are evaluated before the triangle loop) and park a pending leaf range;
+//   LEAF   lanes with a pending range test ONE triangle.
+// Each iteration the warp votes (ballots) which phase to run: a phase runs when enough lanes wait for it or nothing
+// else can run. Traversal stacks live in shared memory, one column per thread (the reference's layout).
+struct TraverseTuning { int setupThreshold; int leafThreshold; };
+
+template <bool STATS>
+__global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, TraverseTuning tune) {
+    extern __shared__ uint32_t s_stack[];
+    uint32_t* stack = s_stack + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t laneLt = (1u << lane) - 1u;
+    const uint32_t count = *a.count;
+    const DeviceScene& sc = a.sc;
+    enum { ST_SETUP = 0, ST_BOX = 1, ST_LEAF = 2, ST_EXIT = 3 };
+
+    int state = ST_SETUP;
+    bool haveRay = false, finished = false, blasHit = false;
+    uint32_t gid = 0, inst = 0, curXf = 0, hitXf = 0;
+    f3 wo = mk3(0, 0, 0), wd = mk3(0, 0, 1);
+    f3 lo = wo, ld = wd, inv = wd;
+    HitRec hit;
+    hit.bx = hit.by = 0.0f; hit.t = 0.0f; hit.tri = ~0u;
+    const float4* nodes = sc.nodes;
+    uint32_t triOffset = 0, top = 2, sp = 0, first = 0, end = 0;
+    uint32_t S = 0, T = 0, I = 0, H = 0;
+    float cost = 0.0f;
+
+    for (;;) {
+        const uint32_t mSetup = __ballot_sync(0xffffffffu, state == ST_SETUP);
+        const uint32_t mBox = __ballot_sync(0xffffffffu, state == ST_BOX);
+        const uint32_t mLeaf = __ballot_sync(0xffffffffu, state == ST_LEAF);
+        if ((mSetup | mBox | mLeaf) == 0u) break;
+
+        if (mSetup && (__popc(mSetup) >= tune.setupThreshold || (mBox | mLeaf) == 0u)) {
+            // ------------------------------------------------------------------ SETUP
+            const bool mine = state == ST_SETUP;
+            if (mine && haveRay && inst >= sc.instanceCount) {
+                reinterpret_cast<float4*>(a.hits)[gid] = make_float4(hit.bx, hit.by, hit.t, __uint_as_float(hit.tri));
+                a.hitXform[gid] = hitXf;
+                if (STATS) {
+                    a.debugCost[gid] = cost;
+                    if (hit.tri != ~0u) H++;
+                }
+                haveRay = false;
+            }
+            const bool needFetch = mine && !haveRay;
+            const uint32_t fm = __ballot_sync(0xffffffffu, needFetch);
+            if (fm) {
+                const int leader = __ffs(fm) - 1;
+                uint32_t base = 0;
+                if ((int)lane == leader) base = atomicAdd(a.ticket, (uint32_t)__popc(fm));
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (needFetch) {
+                    gid = base + __popc(fm & laneLt);
+                    if (gid < count) {
+                        const uint32_t src = a.perm ? a.perm[gid] : gid;
+                        const float4* spp = reinterpret_cast<const float4*>(a.state + src);
+                        const float4 s0 = spp[0], s1 = spp[1];
+                        wo = mk3(s0.x, s0.y, s0.z);
+                        wd = decode_unit_vec(s1.x, s1.y);
+                        hit.t = IDK_FLOAT_MAX; hit.tri = ~0u; hit.bx = 0.0f; hit.by = 0.0f;
+                        hitXf = 0;
+                        cost = 0.0f;
+                        if (a.traceLights) {
+                            for (uint32_t i = 0; i < sc.lightCount; i++) {
+                                const GpuLight& L = sc.lights[i];
+                                float tMin, tMx;
+                                if (ray_sphere(wo, wd, mk3(L.Position[0], L.Position[1], L.Position[2]), L.Radius, tMin, tMx) && tMin < hit.t) {
+                                    hit.t = tMin < 0.0f ? tMx : tMin;
+                                    hitXf = i;
+                                    hit.tri = ~0u;
+                                }
+                            }
+                        }
+                        inst = 0;
+                        haveRay = true;
+                    } else {
+                        state = ST_EXIT;
+                    }
+                }
+            }
+            if (mine && haveRay && inst < sc.instanceCount) {
+                const GpuBlasInstance bi = sc.instances[inst];
+                const int nodeOffset = sc.descs[bi.BlasId].NodeOffset;
+                triOffset = (uint32_t)sc.descs[bi.BlasId].TriangleOffset;
+                const float4* xf = sc.xforms + 9 * (size_t)bi.MeshTransformId + 3;
+                const float4 r0 = ldg4(xf), r1 = ldg4(xf + 1), r2 = ldg4(xf + 2);
+                lo = xform_point(r0, r1, r2, wo);
+                ld = xform_vector(r0, r1, r2, wd);
+                inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+                nodes = sc.nodes + 2 * (size_t)nodeOffset;
+                curXf = bi.MeshTransformId;
+                if (STATS) I++;
+                const float4 ra = ldg4(nodes + 2), rb = ldg4(nodes + 3);
+                float tRoot;
+                if (ray_box(lo, inv, ra, rb, tRoot) && tRoot < hit.t) {
+                    state = ST_BOX;
+                    top = 2; sp = 0; blasHit = false; finished = false;
+                } else {
+                    inst++;
+                }
+            }
+        } else if (mLeaf && (__popc(mLeaf) >= tune.leafThreshold || mBox == 0u)) {
+            // ------------------------------------------------------------------ LEAF (one triangle)
+            if (state == ST_LEAF) {
+                const float4* tr = sc.triRec + 3 * (size_t)first;
+                const float4 ta = ldg4(tr), tb = ldg4(tr + 1), tc = ldg4(tr + 2);
+                float bx, by, t;
+                if (ray_triangle(lo, ld, mk3(ta.x, ta.y, ta.z), mk3(ta.w, tb.x, tb.y), mk3(tb.z, tb.w, tc.x), mk3(tc.y, tc.z, tc.w), bx, by, t) && t < hit.t) {
+                    blasHit = true;
+                    hit.tri = first; hit.bx = bx; hit.by = by; hit.t = t;
+                }
+                first++;
+                if (first == end) {
+                    if (finished) {
+                        if (blasHit) hitXf = curXf;
+                        inst++;
+                        state = ST_SETUP;
+                    } else {
+                        state = ST_BOX;
+                    }
+                }
+            }
+        } else {
+            // ------------------------------------------------------------------ BOX (one sibling pair)
+            if (state == ST_BOX) {
+                if (STATS) { S++; cost += 1.0f; }
+                const float4* np = nodes + 2 * (size_t)top;
+                const float4 lA = ldg4(np), lB = ldg4(np + 1), rA = ldg4(np + 2), rB = ldg4(np + 3);
+                const int lChild = __float_as_int(lA.w), lCount = __float_as_int(lB.w);
+                const int rChild = __float_as_int(rA.w), rCount = __float_as_int(rB.w);
+                float tMinLeft, tMinRight;
+                const bool hitLeft = ray_box(lo, inv, lA, lB, tMinLeft) && tMinLeft <= hit.t;
+                const bool hitRight = ray_box(lo, inv, rA, rB, tMinRight) && tMinRight <= hit.t;
+                const bool intersectLeft = hitLeft && lCount > 0;
+                const bool intersectRight = hitRight && rCount > 0;
+                bool pending = false;
+                if (intersectLeft || intersectRight) {
+                    first = (intersectLeft ? (uint32_t)lChild : (uint32_t)rChild) + triOffset;
+                    end = (!intersectRight ? (uint32_t)(lChild + lCount) : (uint32_t)(rChild + rCount)) + triOffset;
+                    if (STATS) { T += end - first; cost += (float)(end - first) * 1.1f; }
+                    pending = first < end;
+                }
+                const bool traverseLeft = hitLeft && lCount == 0;
+                const bool traverseRight = hitRight && rCount == 0;
+                if (traverseLeft || traverseRight) {
+                    if (traverseLeft && traverseRight) {
+                        const bool leftCloser = tMinLeft < tMinRight;
+                        top = leftCloser ? (uint32_t)lChild : (uint32_t)rChild;
+                        stack[(sp++) * IDK_BLOCK] = leftCloser ? (uint32_t)rChild : (uint32_t)lChild;
+                    } else {
+                        top = traverseLeft ? (uint32_t)lChild : (uint32_t)rChild;
+                    }
+                } else if (sp == 0) {
+                    finished = true;
+                } else {
+                    top = stack[(--sp) * IDK_BLOCK];
+                }
+                if (pending) {
+                    state = ST_LEAF;
+                } else if (finished) {
+                    if (blasHit) hitXf = curXf;
+                    inst++;
+                    state = ST_SETUP;
+                }
             }
         }
     }

@@ -4,6 +4,7 @@
 // (alive counts stay on the device, like the reference's indirect dispatch).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -50,12 +51,15 @@ struct IdkPtCtx {
     DevBuf tileStatus;             // u64 per tile
     DevBuf counters;               // TraceCounters
     DevBuf keys, perm;             // ray sorting
+    DevBuf countLog;               // per-sample copies of the alive counts (stats only)
     IdkSortScratch sortScratch;
     uint32_t epoch = 0;
     bool exportEnabled = false;
 
     // launch configuration
     int traverseBlocks = 0, traverseBlocksStats = 0, shadeBlocks = 0, traceRaysBlocks = 0;
+    int traverseVariant = 2;       // 2 = k_traverse2 (phase-scheduled warps), 1 = k_traverse (one ray per lane, reference loop)
+    TraverseTuning tune = {8, 8};
     size_t stackBytes = 0;
 
     std::vector<cudaEvent_t> events;
@@ -114,11 +118,20 @@ static int configure_launches(IdkPtCtx* ctx) {
     CK(cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
+    CK(cudaFuncSetAttribute(k_traverse2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
+    CK(cudaFuncSetAttribute(k_traverse2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     int n = 0;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
-    ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, IDK_BLOCK, ctx->stackBytes));
-    ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
+    if (ctx->traverseVariant == 1) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
+        ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, IDK_BLOCK, ctx->stackBytes));
+        ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
+    } else {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false>, IDK_BLOCK, ctx->stackBytes));
+        ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true>, IDK_BLOCK, ctx->stackBytes));
+        ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
+    }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_rays, IDK_BLOCK, ctx->stackBytes));
     ctx->traceRaysBlocks = std::max(1, n) * ctx->smCount;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade, IDK_BLOCK, 0));
@@ -192,6 +205,10 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
         delete ctx;
         return fail(nullptr, IDKPT_ERR_CUDA, "idkpt_create: cudaStreamCreate failed");
     }
+    // developer knobs (kernel variant / scheduling thresholds); results are identical for every setting
+    if (const char* v = getenv("IDKPT_TRAVERSE_VARIANT")) ctx->traverseVariant = atoi(v) == 1 ? 1 : 2;
+    if (const char* v = getenv("IDKPT_TUNE_SETUP")) ctx->tune.setupThreshold = std::max(1, std::min(32, atoi(v)));
+    if (const char* v = getenv("IDKPT_TUNE_LEAF")) ctx->tune.leafThreshold = std::max(1, std::min(32, atoi(v)));
     compute_tile_rows(ctx);
     int rc = allocate_wavefront(ctx);
     if (rc != IDKPT_OK) {
@@ -212,7 +229,7 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
                      &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->state[0], &ctx->state[1], &ctx->aov[0],
                      &ctx->aov[1], &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
                      &ctx->aovNormalFinal, &ctx->exportRays, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
-                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->perm};
+                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->perm, &ctx->countLog};
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ctx->sortScratch);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
@@ -435,7 +452,7 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
     uint32_t* tickets = (uint32_t*)ctx->tickets.p;
     uint32_t launches = 0, traverseLaunches = 0;
     std::vector<uint32_t> hostCounts((size_t)st->SamplesPerPixel * (IDKPT_MAX_RAY_DEPTH + 1), 0);
-    DevBuf countLog;   // per-sample copy of counts for the stats (device-side, read once at the end)
+    DevBuf& countLog = ctx->countLog;   // per-sample copy of counts for the stats (device-side, read once at the end)
     if (stats) CK(ensure(countLog, hostCounts.size() * sizeof(uint32_t)));
     if (wantStats) CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(TraceCounters), ctx->stream));
 
@@ -444,10 +461,9 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
 
     for (int s = 0; s < st->SamplesPerPixel; s++) {
         f.accumulatedSamples = ctx->accumulatedSamples;
-        CK(cudaMemsetAsync(counts, 0, ctx->countsDev.bytes, ctx->stream));
-        CK(cudaMemsetAsync(tickets, 0, ctx->tickets.bytes, ctx->stream));
-        // counts[0] = n (every pixel of the tile traces a primary ray)
-        CK(cudaMemcpyAsync(counts, &n, sizeof(uint32_t), cudaMemcpyHostToDevice, ctx->stream));
+        // zero the alive counts and work tickets, counts[0] = n (every pixel of the tile traces a primary ray)
+        k_init_sample<<<1, 256, 0, ctx->stream>>>(counts, IDKPT_MAX_RAY_DEPTH + 1, tickets, 2 * (IDKPT_MAX_RAY_DEPTH + 1), n);
+        launches++;
 
         size_t e0 = ev.begin();
         k_raygen<<<rgGrid, rgBlock, 0, ctx->stream>>>(f, (PathState*)ctx->state[0].p);
@@ -481,8 +497,13 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             ta.counters = (TraceCounters*)ctx->counters.p;
             ta.traceLights = st->Gpu.DoTraceLights;
             e0 = ev.begin();
-            if (wantStats) k_traverse<true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
-            else k_traverse<false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
+            if (ctx->traverseVariant == 1) {
+                if (wantStats) k_traverse<true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
+                else k_traverse<false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
+            } else {
+                if (wantStats) k_traverse2<true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta, ctx->tune);
+                else k_traverse2<false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta, ctx->tune);
+            }
             ev.end(e0, 0);
             launches++;
             traverseLaunches++;
@@ -533,7 +554,6 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
     CK(cudaGetLastError());
     cudaError_t se = cudaStreamSynchronize(ctx->stream);
     if (se != cudaSuccess) {
-        release(countLog);
         ctx->lastError = std::string("idkpt_compute: kernel execution failed: ") + cudaGetErrorString(se);
         return IDKPT_ERR_CUDA;
     }
@@ -568,7 +588,6 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
         stats->KernelLaunches = launches;
         stats->TraverseLaunches = traverseLaunches;
     }
-    release(countLog);
     return IDKPT_OK;
 }
 

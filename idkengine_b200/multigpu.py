@@ -16,25 +16,47 @@ def max_tile_rows(height, stripe, count):
     return max(len(tile_rows(height, stripe, i, count)) for i in range(max(count, 1)))
 
 
+class TileGatherer:
+    """Pre-allocated single-collective gather of tile rows into the full image (one all_gather + one index_select)."""
+
+    def __init__(self, height, width, channels, stripe, world, device, dtype=None, group=None):
+        import torch
+        self.world, self.group, self.height = world, group, height
+        dtype = dtype or torch.float32
+        self.pad_rows = max_tile_rows(height, stripe, world)
+        self.send = torch.zeros((self.pad_rows, width, channels), dtype=dtype, device=device)
+        self.recv = torch.empty((world, self.pad_rows, width, channels), dtype=dtype, device=device)
+        # source row (in the flattened [world*pad_rows] receive buffer) of every image row
+        src = np.zeros(height, np.int64)
+        for r in range(world):
+            rows = tile_rows(height, stripe, r, world)
+            src[rows] = r * self.pad_rows + np.arange(len(rows))
+        self.src = torch.as_tensor(src, device=device)
+        self.full = torch.empty((height, width, channels), dtype=dtype, device=device)
+
+    def gather(self, local_rows):
+        import torch
+        import torch.distributed as dist
+        if self.world <= 1:
+            return local_rows
+        n = local_rows.shape[0]
+        send = local_rows if n == self.pad_rows and local_rows.is_contiguous() else self.send
+        if send is self.send:
+            self.send[:n].copy_(local_rows)
+        if local_rows.is_cuda:
+            dist.all_gather_into_tensor(self.recv.view(-1), send.view(-1), group=self.group)
+        else:
+            dist.all_gather(list(self.recv.unbind(0)), send, group=self.group)
+        torch.index_select(self.recv.view(self.world * self.pad_rows, *self.recv.shape[2:]), 0, self.src, out=self.full)
+        return self.full
+
+
 def all_gather_tiles(local_rows, height, stripe, world, group=None):
-    """local_rows: torch tensor [rows_local, W, C] on this rank's device (compact tile rows).
-    Returns the full [height, W, C] image on every rank after a single all_gather."""
-    import torch
-    import torch.distributed as dist
+    """Convenience wrapper (allocates): full [height, W, C] image on every rank after a single all_gather."""
     if world <= 1:
         return local_rows
-    pad_rows = max_tile_rows(height, stripe, world)
-    w, c = local_rows.shape[1], local_rows.shape[2]
-    send = torch.zeros((pad_rows, w, c), dtype=local_rows.dtype, device=local_rows.device)
-    send[: local_rows.shape[0]] = local_rows
-    recv = torch.empty((world, pad_rows, w, c), dtype=local_rows.dtype, device=local_rows.device)
-    dist.all_gather_into_tensor(recv.view(-1), send.view(-1), group=group) if local_rows.is_cuda else \
-        dist.all_gather(list(recv.unbind(0)), send, group=group)
-    full = torch.empty((height, w, c), dtype=local_rows.dtype, device=local_rows.device)
-    for r in range(world):
-        rows = torch.as_tensor(tile_rows(height, stripe, r, world), device=local_rows.device, dtype=torch.long)
-        full[rows] = recv[r, : len(rows)]
-    return full
+    g = TileGatherer(height, local_rows.shape[1], local_rows.shape[2], stripe, world, local_rows.device, local_rows.dtype, group)
+    return g.gather(local_rows).clone()
 
 
 class DeviceArray:

@@ -1086,3 +1086,5 @@ ORACLE_API void oracle_encode_decode(const float* dirs, uint64_t n, float* enc2,
 ORACLE_API uint32_t oracle_pcg(uint32_t seed, uint32_t* nextSeed) { uint32_t s = seed; uint32_t r = GetPCGHash(s); *nextSeed = s; return r; }
 
 } // extern "C"
+
+#include "oracle_vxgi.inc"

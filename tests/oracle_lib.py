@@ -121,3 +121,89 @@ def path_trace(scene, frame, settings, width, height, sky=(0.6, 0.7, 0.9), tile=
     out = PathTraceResult()
     out.result, out.albedo, out.normal, out.rays, out.accumulated, out.stats = res, alb, nrm, rays, acc.value, stats
     return out
+
+
+# ----------------------------------------------------------------------------------------------- VXGI
+def _vx_declare():
+    L = lib()
+    from idkengine_b200 import vxgi
+    P = ctypes.POINTER
+    vp, u64, i32 = ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32
+    L.oracle_vx_voxelize.restype = i32
+    L.oracle_vx_voxelize.argtypes = [P(capi.IdkPtSceneDesc), P(vxgi.IdkVxCreateInfo), vp, u64, P(u64), i32]
+    L.oracle_vx_cone_trace.restype = i32
+    L.oracle_vx_cone_trace.argtypes = [P(vxgi.IdkVxCreateInfo), vp, vp, P(vxgi.IdkVxConeSettings), vp, vp, vp, i32, i32, vp, vp, P(u64), i32]
+    L.oracle_half_roundtrip.argtypes = [vp, u64, vp, vp]
+    L.oracle_det_log2.argtypes = [vp, u64, vp]
+    return L
+
+
+def vx_voxelize(scene, ci, threads=None):
+    """Returns (list of float16 [d,h,w,4] arrays per level, concatenated raw uint16 chain, fragment count)."""
+    from idkengine_b200 import vxgi
+    L = _vx_declare()
+    sizes = vxgi.level_sizes(ci)
+    total = sum(w * h * d for w, h, d in sizes)
+    raw = np.zeros(total * 4, np.uint16)
+    d, keep = capi.scene_desc(scene)
+    frags = ctypes.c_uint64()
+    n = L.oracle_vx_voxelize(ctypes.byref(d), ctypes.byref(ci), raw.ctypes.data, total, ctypes.byref(frags), threads or default_threads())
+    assert n == len(sizes), n
+    levels, off = [], 0
+    for (w, h, dd) in sizes:
+        k = w * h * dd * 4
+        levels.append(raw[off:off + k].view(np.float16).reshape(dd, h, w, 4))
+        off += k
+    return levels, raw, frags.value
+
+
+def vx_cone_trace(ci, raw_chain, frame, settings, depth, normal_rg, metal_rough, sky=(0.6, 0.7, 0.9), threads=None):
+    L = _vx_declare()
+    h, w = depth.shape
+    out = np.zeros((h, w, 4), np.float32)
+    skyc = np.array(sky, np.float32)
+    steps = ctypes.c_uint64()
+    depth = np.ascontiguousarray(depth, np.float32)
+    nrg = np.ascontiguousarray(normal_rg, np.float32)
+    mr = np.ascontiguousarray(metal_rough, np.float32)
+    rc = L.oracle_vx_cone_trace(ctypes.byref(ci), raw_chain.ctypes.data, frame.ctypes.data, ctypes.byref(settings), depth.ctypes.data,
+                                nrg.ctypes.data, mr.ctypes.data, w, h, skyc.ctypes.data, out.ctypes.data, ctypes.byref(steps),
+                                threads or default_threads())
+    assert rc == 0
+    return out, steps.value
+
+
+def synth_gbuffer(scene, frame, width, height):
+    """G-buffer for the cone tracer synthesised from the path tracer's first hit:
+    depth = ProjView-projected hit point (1.0 = sky), normal = octahedral geometric normal facing the camera,
+    metallic/roughness from the hit material."""
+    rays = gui_test_rays(frame, width, height)
+    # pixel centres instead of Gui.Test's pixel corners
+    hits = trace_rays(scene, rays)
+    hit = hits["TriangleId"] != 0xFFFFFFFF
+    o = rays["Origin"].astype(np.float64)
+    d = rays["Direction"].astype(np.float64)
+    pos = o + d * hits["T"][:, None].astype(np.float64)
+    pv = frame["ProjView"][0].astype(np.float64).reshape(4, 4)      # OpenTK rows: clip = [p,1] @ pv
+    clip = np.concatenate([pos, np.ones((len(pos), 1))], 1) @ pv
+    depth = np.where(hit, clip[:, 2] / clip[:, 3], 1.0).astype(np.float32)
+    depth = np.where(hit & (depth >= 1.0), np.float32(0.999999), depth)
+    tri = scene.blas_triangles[np.where(hit, hits["TriangleId"], 0)]
+    P = scene.positions
+    p0 = np.stack([P["x"][tri["X"]], P["y"][tri["X"]], P["z"][tri["X"]]], 1).astype(np.float64)
+    p1 = np.stack([P["x"][tri["Y"]], P["y"][tri["Y"]], P["z"][tri["Y"]]], 1).astype(np.float64)
+    p2 = np.stack([P["x"][tri["Z"]], P["y"][tri["Z"]], P["z"][tri["Z"]]], 1).astype(np.float64)
+    n = np.cross(p1 - p0, p2 - p0)
+    inv = scene.mesh_transforms["InvModelMatrix"][hits["MeshTransformId"]][:, :, :3].astype(np.float64)   # [N,3,3]
+    n = np.einsum("nji,nj->ni", inv, n)                                # transpose(inv) * n
+    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)
+    n = np.where((np.sum(n * d, 1) > 0)[:, None], -n, n)
+    # EncodeUnitVec (Compression.glsl:54-61)
+    m = n / np.sum(np.abs(n), 1, keepdims=True)
+    wrap = (1.0 - np.abs(m[:, [1, 0]])) * np.where(m[:, :2] < 0, -1.0, 1.0)
+    xy = np.where((m[:, 2] > 0)[:, None], m[:, :2], wrap)
+    nrg = (xy * 0.5 + 0.5).astype(np.float32)
+    mesh = scene.meshes[tri["MeshId"]]
+    mat = scene.materials[mesh["MaterialId"]]
+    mr = np.stack([np.clip(mat["MetallicFactor"] + mesh["SpecularBias"], 0, 1), np.clip(mat["RoughnessFactor"] + mesh["RoughnessBias"], 0, 1)], 1).astype(np.float32)
+    return depth.reshape(height, width), nrg.reshape(height, width, 2), mr.reshape(height, width, 2)

@@ -1,0 +1,115 @@
+"""VXGI passes (BASELINE.json configs[4]): CPU oracle sanity (not gpu) and CUDA vs oracle parity (gpu)."""
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from idkengine_b200 import scenes, vxgi
+
+GRID_MIN, GRID_MAX = (-1.2, -0.2, -1.2), (1.2, 2.2, 1.2)
+
+
+def lit_cornell():
+    scene, cam = scenes.cornell_1k(threads=1)
+    scene.add_light((0.0, 1.6, 0.3), (6.0, 5.5, 5.0), 0.2)
+    scene.add_light((-0.6, 0.5, 0.6), (0.5, 0.8, 3.0), 0.1)
+    return scene, cam
+
+
+def test_half_conversion_and_log2():
+    L = ol._vx_declare()
+    x = np.concatenate([np.linspace(0, 70000, 20001), 10.0 ** np.linspace(-9, 5, 3001), [65504, 65519.9, 65520, 1e-8, 6e-8, 5.96e-8, 2.98e-8]]).astype(np.float32)
+    h, back = np.zeros(len(x), np.uint16), np.zeros(len(x), np.float32)
+    L.oracle_half_roundtrip(x.ctypes.data, len(x), h.ctypes.data, back.ctypes.data)
+    with np.errstate(over="ignore"):
+        ref = x.astype(np.float16)
+    assert np.array_equal(h, ref.view(np.uint16))
+    assert np.array_equal(back, ref.astype(np.float32))
+    v = np.linspace(1.0, 600.0, 50001).astype(np.float32)
+    y = np.zeros_like(v)
+    L.oracle_det_log2(v.ctypes.data, len(v), y.ctypes.data)
+    assert np.abs(y - np.log2(v.astype(np.float64))).max() < 2e-6
+
+
+def test_oracle_voxelize_and_mip_properties():
+    scene, cam = lit_cornell()
+    ci = vxgi.create_info(48, GRID_MIN, GRID_MAX)
+    levels, raw, frags = ol.vx_voxelize(scene, ci)
+    assert [l.shape[0] for l in levels] == [48, 24, 12, 6, 3, 1]
+    l0 = levels[0].astype(np.float32)
+    occ = l0[..., 3] == 1.0
+    assert frags >= occ.sum() > 48 * 48          # at least the walls
+    assert np.all(l0[~occ] == 0) and np.all(l0[occ][:, :3] >= 0)
+    # floor (y ~ 0) and back wall (z ~ -1) are solid slabs of voxels
+    y0 = int((0.0 - GRID_MIN[1]) / (GRID_MAX[1] - GRID_MIN[1]) * 48)
+    assert occ[8:40, y0 - 1:y0 + 1, 8:40].any(axis=1).mean() > 0.95   # the plane sits on a voxel boundary
+    # the emitter voxels are the brightest
+    assert l0[..., :3].max() > 10.0
+    # mip level 1 texel = ((7-tap) of level-0 box averages): alpha in [0,1], energy roughly conserved
+    l1 = levels[1].astype(np.float32)
+    assert l1[..., 3].max() <= 1.0 and abs(l1[..., 3].mean() - l0[..., 3].mean()) < 0.02
+    assert 0 < levels[-1].astype(np.float32)[0, 0, 0, 3] < 1
+
+
+def test_oracle_cone_trace_plausible():
+    scene, cam = lit_cornell()
+    ci = vxgi.create_info(48, GRID_MIN, GRID_MAX)
+    levels, raw, _ = ol.vx_voxelize(scene, ci)
+    w, h = 64, 48
+    frame = scenes.camera_frame(cam, w, h)
+    depth, nrg, mr = ol.synth_gbuffer(scene, frame, w, h)
+    out, steps = ol.vx_cone_trace(ci, raw, frame, vxgi.default_cone_settings(), depth, nrg, mr)
+    assert np.isfinite(out).all() and steps > w * h
+    assert np.all(out[depth < 1.0][:, 3] == 1.0) and np.all(out[depth == 1.0] == 0)
+    assert out[..., :3].mean() > 0.01
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [48, (40, 56, 32)])
+def test_gpu_voxelize_mip_cone_match_oracle(size):
+    scene, cam = lit_cornell()
+    ci = vxgi.create_info(size, GRID_MIN, GRID_MAX)
+    levels, raw, frags = ol.vx_voxelize(scene, ci)
+    w, h = 96, 64
+    frame = scenes.camera_frame(cam, w, h)
+    depth, nrg, mr = ol.synth_gbuffer(scene, frame, w, h)
+    st = vxgi.default_cone_settings()
+    st.NoiseIndex = 3
+    ref, steps = ol.vx_cone_trace(ci, raw, frame, st, depth, nrg, mr)
+    with vxgi.Voxelizer(size, GRID_MIN, GRID_MAX) as vx:
+        vx.SetScene(scene)
+        s = vx.Render()
+        assert s.Fragments == frags
+        for l, lv in enumerate(levels):
+            g = vx.ReadLevel(l)
+            assert np.array_equal(g.view(np.uint16), lv.view(np.uint16)), f"level {l}"
+        out, cs = vx.ConeTrace(frame, depth, nrg, mr, st)
+        assert cs.ConeSteps == steps
+        assert np.array_equal(out, ref)
+        s2 = vx.Render()        # re-voxelising clears first: same grid
+        assert np.array_equal(vx.ReadLevel(0).view(np.uint16), levels[0].view(np.uint16)) and s2.Fragments == frags
+
+
+@pytest.mark.gpu
+def test_gpu_vxgi_atrium_transformed_scene(atrium_small):
+    scene, cam = atrium_small
+    scene.lights = scene.lights[:0]
+    scene.add_light((0.0, 6.0, 0.0), (40.0, 38.0, 30.0), 0.3)
+    ci = vxgi.create_info(64)
+    levels, raw, frags = ol.vx_voxelize(scene, ci)
+    with vxgi.Voxelizer(64) as vx:
+        vx.SetScene(scene)
+        s = vx.Render()
+        assert s.Fragments == frags
+        for l, lv in enumerate(levels):
+            assert np.array_equal(vx.ReadLevel(l).view(np.uint16), lv.view(np.uint16)), f"level {l}"
+
+
+@pytest.mark.gpu
+def test_gpu_vxgi_errors():
+    scene, cam = lit_cornell()
+    with vxgi.Voxelizer(16, GRID_MIN, GRID_MAX) as vx:
+        with pytest.raises(vxgi.IdkVxError, match="idkvx_set_scene has not been called"):
+            vx.Render()
+        scene.lights["PointShadowIndex"][0] = 0
+        with pytest.raises(vxgi.IdkVxError, match="point-shadowed"):
+            vx.SetScene(scene)
