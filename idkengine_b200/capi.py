@@ -115,10 +115,20 @@ def scene_desc(scene):
     return d, keep
 
 
-def sky_desc(color=(0.6, 0.7, 0.9)):
+def sky_desc(color=(0.6, 0.7, 0.9), faces=None):
+    """Constant sky colour, or a cubemap: faces = float32 array [6, N, N, 4] (+X,-X,+Y,-Y,+Z,-Z)."""
     s = IdkPtSkyDesc()
+    if isinstance(color, np.ndarray) and color.ndim == 4:
+        faces, color = color, (0.0, 0.0, 0.0)
     s.Color[0], s.Color[1], s.Color[2] = color
     s.FaceSize = 0
+    if faces is not None:
+        faces = np.ascontiguousarray(faces, np.float32)
+        assert faces.ndim == 4 and faces.shape[0] == 6 and faces.shape[1] == faces.shape[2] and faces.shape[3] == 4
+        s.FaceSize = faces.shape[1]
+        for i in range(6):
+            s.Faces[i] = faces[i].ctypes.data
+        s._keep = faces
     return s
 
 

@@ -29,7 +29,13 @@ struct DeviceScene {
     uint32_t lightCount;
     float skyR, skyG, skyB;
     int stackSize;
+    const float4* skyFaces;       // 6 faces x skyFaceSize^2 rgba32f texels (+X,-X,+Y,-Y,+Z,-Z), null = constant colour
+    int skyFaceSize;
+    const float4* tlasNodes;      // 2 x float4 per GpuTlasNode, root at 0 (USE_TLAS path, BVHIntersect.glsl:205-272)
+    int useTlas;
 };
+
+#define IDK_TLAS_STACK_SIZE 24   // BVHIntersect.glsl:4
 
 // 64-byte per-slot path state (slot = position in the alive list of the current bounce).
 struct __align__(16) PathState {
@@ -71,8 +77,86 @@ __global__ void k_prepare_triangles(const int4* __restrict__ tris, const float* 
 }
 
 // ------------------------------------------------------------------------------------------------
-// Closest-hit traversal of one ray. `stack` points at this thread's column of the shared stack
-// (stride IDK_BLOCK), exactly the reference's `shared uint BlasTraversalStack[SIZE][LOCAL_SIZE]`.
+// IntersectBlas (BVHIntersect.glsl:27-105) for one local-space ray. `stack` points at this thread's column of the
+// shared stack (stride IDK_BLOCK), exactly the reference's `shared uint BlasTraversalStack[SIZE][LOCAL_SIZE]`.
+template <bool STATS>
+__device__ __forceinline__ bool intersect_blas(const DeviceScene& sc, const float4* nodes, uint32_t triOffset, f3 lo, f3 ld, f3 inv,
+                                               bool rootTest, uint32_t* stack, HitRec& hit, uint32_t& S, uint32_t& T, float& cost) {
+    float tMinLeft, tMinRight;
+    if (rootTest) {   // #if !USE_TLAS
+        const float4 a = ldg4(nodes + 2), b = ldg4(nodes + 3);   // root = node 1
+        if (!(ray_box(lo, inv, a, b, tMinLeft) && tMinLeft < hit.t)) return false;
+    }
+    bool blasHit = false;
+    uint32_t sp = 0;
+    uint32_t top = 2;
+    while (true) {
+        if (STATS) { S++; cost += 1.0f; }
+        const float4* np = nodes + 2 * (size_t)top;
+        const float4 lA = ldg4(np), lB = ldg4(np + 1), rA = ldg4(np + 2), rB = ldg4(np + 3);
+        const int lChild = __float_as_int(lA.w), lCount = __float_as_int(lB.w);
+        const int rChild = __float_as_int(rA.w), rCount = __float_as_int(rB.w);
+
+        const bool hitLeft = ray_box(lo, inv, lA, lB, tMinLeft) && tMinLeft <= hit.t;
+        const bool hitRight = ray_box(lo, inv, rA, rB, tMinRight) && tMinRight <= hit.t;
+
+        const bool intersectLeft = hitLeft && lCount > 0;
+        const bool intersectRight = hitRight && rCount > 0;
+        if (intersectLeft || intersectRight) {
+            uint32_t first = intersectLeft ? (uint32_t)lChild : (uint32_t)rChild;
+            uint32_t end = !intersectRight ? (uint32_t)(lChild + lCount) : (uint32_t)(rChild + rCount);
+            first += triOffset;
+            end += triOffset;
+            if (STATS) { T += end - first; cost += (float)(end - first) * 1.1f; }
+            for (uint32_t i = first; i < end; i++) {
+                const float4* tr = sc.triRec + 3 * (size_t)i;
+                const float4 a = ldg4(tr), b = ldg4(tr + 1), c = ldg4(tr + 2);
+                float bx, by, t;
+                if (ray_triangle(lo, ld, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), bx, by, t) && t < hit.t) {
+                    blasHit = true;
+                    hit.tri = i;
+                    hit.bx = bx;
+                    hit.by = by;
+                    hit.t = t;
+                }
+            }
+        }
+
+        const bool traverseLeft = hitLeft && lCount == 0;
+        const bool traverseRight = hitRight && rCount == 0;
+        if (traverseLeft || traverseRight) {
+            if (traverseLeft && traverseRight) {
+                const bool leftCloser = tMinLeft < tMinRight;
+                top = leftCloser ? (uint32_t)lChild : (uint32_t)rChild;
+                stack[(sp++) * IDK_BLOCK] = leftCloser ? (uint32_t)rChild : (uint32_t)lChild;
+            } else {
+                top = traverseLeft ? (uint32_t)lChild : (uint32_t)rChild;
+            }
+        } else {
+            if (sp == 0) break;
+            top = stack[(--sp) * IDK_BLOCK];
+        }
+    }
+    return blasHit;
+}
+
+// One BLAS instance: local ray (Ray.glsl:7-12) + IntersectBlas.
+template <bool STATS>
+__device__ __forceinline__ void trace_instance(const DeviceScene& sc, uint32_t inst, f3 o, f3 d, bool rootTest, uint32_t* stack,
+                                               HitRec& hit, uint32_t& hitXform, uint32_t& S, uint32_t& T, uint32_t& I, float& cost) {
+    const GpuBlasInstance bi = sc.instances[inst];
+    const int nodeOffset = sc.descs[bi.BlasId].NodeOffset;
+    const uint32_t triOffset = (uint32_t)sc.descs[bi.BlasId].TriangleOffset;
+    const float4* xf = sc.xforms + 9 * (size_t)bi.MeshTransformId + 3;   // InvModelMatrix rows
+    const float4 r0 = ldg4(xf), r1 = ldg4(xf + 1), r2 = ldg4(xf + 2);
+    const f3 lo = xform_point(r0, r1, r2, o);
+    const f3 ld = xform_vector(r0, r1, r2, d);
+    const f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
+    if (STATS) I++;
+    if (intersect_blas<STATS>(sc, sc.nodes + 2 * (size_t)nodeOffset, triOffset, lo, ld, inv, rootTest, stack, hit, S, T, cost)) hitXform = bi.MeshTransformId;
+}
+
+// TraceRay (BVHIntersect.glsl:183-291): lights, then the instance loop (default) or the TLAS walk.
 template <bool STATS>
 __device__ __forceinline__ void trace_closest(const DeviceScene& sc, f3 o, f3 d, float tMax, bool traceLights,
                                               uint32_t* stack, HitRec& hit, uint32_t& hitXform,
@@ -95,75 +179,40 @@ __device__ __forceinline__ void trace_closest(const DeviceScene& sc, f3 o, f3 d,
         }
     }
 
-    for (uint32_t inst = 0; inst < sc.instanceCount; inst++) {
-        const GpuBlasInstance bi = sc.instances[inst];
-        const int nodeOffset = sc.descs[bi.BlasId].NodeOffset;
-        const uint32_t triOffset = (uint32_t)sc.descs[bi.BlasId].TriangleOffset;
-        const float4* xf = sc.xforms + 9 * (size_t)bi.MeshTransformId + 3;   // InvModelMatrix rows
-        const float4 r0 = ldg4(xf), r1 = ldg4(xf + 1), r2 = ldg4(xf + 2);
-        const f3 lo = xform_point(r0, r1, r2, o);
-        const f3 ld = xform_vector(r0, r1, r2, d);
-        const f3 inv = mk3(1.0f / ld.x, 1.0f / ld.y, 1.0f / ld.z);
-        const float4* nodes = sc.nodes + 2 * (size_t)nodeOffset;
-        if (STATS) I++;
-
-        float tMinLeft, tMinRight;
-        {
-            const float4 a = ldg4(nodes + 2), b = ldg4(nodes + 3);   // root = node 1
-            if (!(ray_box(lo, inv, a, b, tMinLeft) && tMinLeft < hit.t)) continue;
-        }
-
-        bool blasHit = false;
-        uint32_t sp = 0;
-        uint32_t top = 2;
+    if (sc.useTlas) {
+        const f3 inv = mk3(1.0f / d.x, 1.0f / d.y, 1.0f / d.z);
+        uint32_t tstack[IDK_TLAS_STACK_SIZE];
+        uint32_t sp = 0, top = 0;
         while (true) {
-            if (STATS) { S++; cost += 1.0f; }
-            const float4* np = nodes + 2 * (size_t)top;
-            const float4 lA = ldg4(np), lB = ldg4(np + 1), rA = ldg4(np + 2), rB = ldg4(np + 3);
-            const int lChild = __float_as_int(lA.w), lCount = __float_as_int(lB.w);
-            const int rChild = __float_as_int(rA.w), rCount = __float_as_int(rB.w);
-
-            const bool hitLeft = ray_box(lo, inv, lA, lB, tMinLeft) && tMinLeft <= hit.t;
-            const bool hitRight = ray_box(lo, inv, rA, rB, tMinRight) && tMinRight <= hit.t;
-
-            const bool intersectLeft = hitLeft && lCount > 0;
-            const bool intersectRight = hitRight && rCount > 0;
-            if (intersectLeft || intersectRight) {
-                uint32_t first = intersectLeft ? (uint32_t)lChild : (uint32_t)rChild;
-                uint32_t end = !intersectRight ? (uint32_t)(lChild + lCount) : (uint32_t)(rChild + rCount);
-                first += triOffset;
-                end += triOffset;
-                if (STATS) { T += end - first; cost += (float)(end - first) * 1.1f; }
-                for (uint32_t i = first; i < end; i++) {
-                    const float4* tr = sc.triRec + 3 * (size_t)i;
-                    const float4 a = ldg4(tr), b = ldg4(tr + 1), c = ldg4(tr + 2);
-                    float bx, by, t;
-                    if (ray_triangle(lo, ld, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), bx, by, t) && t < hit.t) {
-                        blasHit = true;
-                        hit.tri = i;
-                        hit.bx = bx;
-                        hit.by = by;
-                        hit.t = t;
-                    }
-                }
+            const float4 pA = ldg4(sc.tlasNodes + 2 * (size_t)top);
+            const uint32_t word = __float_as_uint(pA.w);
+            const uint32_t id = word & 0x7FFFFFFFu;
+            if (word >> 31) {
+                trace_instance<STATS>(sc, id, o, d, false, stack, hit, hitXform, S, T, I, cost);
+                if (sp == 0) break;
+                top = tstack[--sp];
+                continue;
             }
-
-            const bool traverseLeft = hitLeft && lCount == 0;
-            const bool traverseRight = hitRight && rCount == 0;
+            const float4 lA = ldg4(sc.tlasNodes + 2 * (size_t)id), lB = ldg4(sc.tlasNodes + 2 * (size_t)id + 1);
+            const float4 rA = ldg4(sc.tlasNodes + 2 * (size_t)id + 2), rB = ldg4(sc.tlasNodes + 2 * (size_t)id + 3);
+            float tMinLeft, tMinRight;
+            const bool traverseLeft = ray_box(o, inv, lA, lB, tMinLeft) && tMinLeft < hit.t;
+            const bool traverseRight = ray_box(o, inv, rA, rB, tMinRight) && tMinRight < hit.t;
             if (traverseLeft || traverseRight) {
                 if (traverseLeft && traverseRight) {
                     const bool leftCloser = tMinLeft < tMinRight;
-                    top = leftCloser ? (uint32_t)lChild : (uint32_t)rChild;
-                    stack[(sp++) * IDK_BLOCK] = leftCloser ? (uint32_t)rChild : (uint32_t)lChild;
+                    top = leftCloser ? id : id + 1;
+                    tstack[sp++] = leftCloser ? id + 1 : id;
                 } else {
-                    top = traverseLeft ? (uint32_t)lChild : (uint32_t)rChild;
+                    top = traverseLeft ? id : id + 1;
                 }
             } else {
                 if (sp == 0) break;
-                top = stack[(--sp) * IDK_BLOCK];
+                top = tstack[--sp];
             }
         }
-        if (blasHit) hitXform = bi.MeshTransformId;
+    } else {
+        for (uint32_t inst = 0; inst < sc.instanceCount; inst++) trace_instance<STATS>(sc, inst, o, d, true, stack, hit, hitXform, S, T, I, cost);
     }
 }
 
@@ -523,6 +572,30 @@ struct Surface {
     bool IsVolumetric, TintOnTransmissive;
 };
 
+// texture(skyBoxUBO.Albedo, dir).rgb: GL cube-map face selection (spec table 8.19), bilinear inside the face, clamp to edge.
+__device__ __forceinline__ f3 sample_sky(const DeviceScene& sc, f3 d) {
+    if (sc.skyFaceSize == 0) return mk3(sc.skyR, sc.skyG, sc.skyB);
+    const int size = sc.skyFaceSize;
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int face;
+    float scc, tc, ma;
+    if (ax >= ay && ax >= az) { face = d.x >= 0.0f ? 0 : 1; scc = d.x >= 0.0f ? -d.z : d.z; tc = -d.y; ma = ax; }
+    else if (ay >= az) { face = d.y >= 0.0f ? 2 : 3; scc = d.x; tc = d.y >= 0.0f ? d.z : -d.z; ma = ay; }
+    else { face = d.z >= 0.0f ? 4 : 5; scc = d.z >= 0.0f ? d.x : -d.x; tc = -d.y; ma = az; }
+    const float s = 0.5f * (scc / ma + 1.0f), t = 0.5f * (tc / ma + 1.0f);
+    const float px = s * (float)size - 0.5f, py = t * (float)size - 0.5f;
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float fx = px - fx0, fy = py - fy0;
+    const int x0 = min(max((int)fx0, 0), size - 1), x1 = min(max((int)fx0 + 1, 0), size - 1);
+    const int y0 = min(max((int)fy0, 0), size - 1), y1 = min(max((int)fy0 + 1, 0), size - 1);
+    const float4* fp = sc.skyFaces + (size_t)face * size * size;
+    const float4 t00 = __ldg(fp + (size_t)y0 * size + x0), t10 = __ldg(fp + (size_t)y0 * size + x1);
+    const float4 t01 = __ldg(fp + (size_t)y1 * size + x0), t11 = __ldg(fp + (size_t)y1 * size + x1);
+    const f3 a = mix3(mk3(t00.x, t00.y, t00.z), mk3(t10.x, t10.y, t10.z), fx);
+    const f3 b = mix3(mk3(t01.x, t01.y, t01.z), mk3(t11.x, t11.y, t11.z), fx);
+    return mix3(a, b, fy);
+}
+
 struct ShadeArgs {
     DeviceScene sc;
     FrameParams f;
@@ -776,7 +849,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_shade(ShadeArgs a) {
                     }
                 }
             } else {
-                const f3 albedo = mk3(sc.skyR, sc.skyG, sc.skyB);
+                const f3 albedo = sample_sky(sc, rayDir);
                 if (a.outputAovs) {
                     const f3 fn = cubemap_face_normal(rayDir);
                     if (a.firstHit) {

@@ -40,8 +40,10 @@ struct IdkPtCtx {
     bool haveScene = false;
     DeviceScene sc = {};
     IdkPtSceneDesc counts = {};    // element counts only (pointers unused)
-    DevBuf nodes, triRec, blasTris, positions, descs, instances, xforms, meshes, materials, vertices, lights;
+    DevBuf nodes, triRec, blasTris, positions, descs, instances, xforms, meshes, materials, vertices, lights, tlas;
     float sky[3] = {0.0f, 0.0f, 0.0f};
+    DevBuf skyFaces;
+    int skyFaceSize = 0;
 
     // wavefront buffers
     DevBuf state[2], aov[2], hits, hitXform, debugCost, radiance, aovAlbedoFinal, aovNormalFinal, exportRays;
@@ -121,7 +123,7 @@ static int configure_launches(IdkPtCtx* ctx) {
     CK(cudaFuncSetAttribute(k_traverse2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_traverse2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     int n = 0;
-    if (ctx->traverseVariant == 1) {
+    if (ctx->traverseVariant == 1 || ctx->sc.useTlas) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
         ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, IDK_BLOCK, ctx->stackBytes));
@@ -226,10 +228,10 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->nodes, &ctx->triRec, &ctx->blasTris, &ctx->positions, &ctx->descs, &ctx->instances, &ctx->xforms,
-                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->state[0], &ctx->state[1], &ctx->aov[0],
+                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->state[0], &ctx->state[1], &ctx->aov[0],
                      &ctx->aov[1], &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
                      &ctx->aovNormalFinal, &ctx->exportRays, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
-                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->perm, &ctx->countLog};
+                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->perm, &ctx->countLog, &ctx->skyFaces};
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ctx->sortScratch);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
@@ -244,7 +246,16 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
         !s->Materials || !s->Vertices || !s->VertexPositions)
         return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: a required array is null");
     if (s->LightCount > IDK_GPU_MAX_UBO_LIGHT_COUNT) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: more than 256 lights");
-    if (s->UseTlas) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_scene: UseTlas=1 is not implemented yet (BVH.GpuUseTlas defaults to false)");
+    if (s->UseTlas) {
+        // TLAS.AllocateRequiredNodes: 2n-1 nodes, root at 0, children adjacent (TLAS.cs:266-269)
+        if (!s->TlasNodes || s->BlasInstanceCount == 0 || s->TlasNodeCount != 2 * s->BlasInstanceCount - 1)
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: UseTlas needs 2*instances-1 TLAS nodes");
+        for (uint64_t i = 0; i < s->TlasNodeCount; i++) {
+            const uint32_t w = s->TlasNodes[i].IsLeafAndChildOrInstanceId, id = w & 0x7FFFFFFFu;
+            if ((w >> 31) ? (id >= s->BlasInstanceCount) : (id <= i || (uint64_t)id + 1 >= s->TlasNodeCount))
+                return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: malformed TLAS node (child / instance id out of range)");
+        }
+    }
     if (s->BlasTriangleCount >= (1ull << 31) || s->BlasNodeCount >= (1ull << 31)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: scene too large");
     // validate indices the kernels will chase (a bad host array must not become a device fault)
     for (uint64_t i = 0; i < s->BlasInstanceCount; i++) {
@@ -279,6 +290,7 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     if ((rc = upload(ctx, ctx->materials, s->Materials, s->MaterialCount * sizeof(GpuMaterial)))) return rc;
     if ((rc = upload(ctx, ctx->vertices, s->Vertices, s->VertexCount * sizeof(GpuVertex)))) return rc;
     if ((rc = upload(ctx, ctx->lights, s->Lights, s->LightCount * sizeof(GpuLight)))) return rc;
+    if ((rc = upload(ctx, ctx->tlas, s->TlasNodes, s->UseTlas ? s->TlasNodeCount * sizeof(GpuTlasNode) : 0))) return rc;
     CK(ensure(ctx->triRec, std::max<size_t>(s->BlasTriangleCount, 1) * 48));
 
     // triangle vertex ids must index the position / vertex arrays
@@ -309,7 +321,11 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     sc.instanceCount = (uint32_t)s->BlasInstanceCount;
     sc.lightCount = (uint32_t)s->LightCount;
     sc.skyR = ctx->sky[0]; sc.skyG = ctx->sky[1]; sc.skyB = ctx->sky[2];
+    sc.skyFaces = ctx->skyFaceSize ? (const float4*)ctx->skyFaces.p : nullptr;
+    sc.skyFaceSize = ctx->skyFaceSize;
     sc.stackSize = std::max(1, s->BlasStackSize);
+    sc.tlasNodes = (const float4*)ctx->tlas.p;
+    sc.useTlas = s->UseTlas ? 1 : 0;
     ctx->counts = *s;
     if ((rc = configure_launches(ctx))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -347,9 +363,20 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
 
 IDKPT_API int idkpt_set_sky(IdkPtCtx* ctx, const IdkPtSkyDesc* sky) {
     if (!ctx || !sky) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_sky: null argument");
-    if (sky->FaceSize != 0) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_sky: cubemap faces are not implemented yet (constant colour only)");
+    if (sky->FaceSize < 0 || sky->FaceSize > 8192) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_sky: invalid FaceSize");
+    CK(cudaSetDevice(ctx->device));
+    if (sky->FaceSize > 0) {
+        const size_t faceBytes = (size_t)sky->FaceSize * sky->FaceSize * 16;
+        for (int i = 0; i < 6; i++) if (!sky->Faces[i]) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_sky: a cubemap face is null");
+        CK(ensure(ctx->skyFaces, 6 * faceBytes));
+        for (int i = 0; i < 6; i++) CK(cudaMemcpyAsync((char*)ctx->skyFaces.p + i * faceBytes, sky->Faces[i], faceBytes, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->skyFaceSize = sky->FaceSize;
     for (int i = 0; i < 3; i++) ctx->sky[i] = sky->Color[i];
     ctx->sc.skyR = ctx->sky[0]; ctx->sc.skyG = ctx->sky[1]; ctx->sc.skyB = ctx->sky[2];
+    ctx->sc.skyFaces = ctx->skyFaceSize ? (const float4*)ctx->skyFaces.p : nullptr;
+    ctx->sc.skyFaceSize = ctx->skyFaceSize;
     ctx->accumulatedSamples = 0;
     return IDKPT_OK;
 }
@@ -497,7 +524,7 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             ta.counters = (TraceCounters*)ctx->counters.p;
             ta.traceLights = st->Gpu.DoTraceLights;
             e0 = ev.begin();
-            if (ctx->traverseVariant == 1) {
+            if (ctx->traverseVariant == 1 || ctx->sc.useTlas) {
                 if (wantStats) k_traverse<true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
                 else k_traverse<false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
             } else {

@@ -56,6 +56,10 @@ def lib():
         L.idkhost_blas_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.idkhost_blas_free.restype = None
         L.idkhost_blas_free.argtypes = [ctypes.c_void_p]
+        L.idkhost_transform_box.restype = None
+        L.idkhost_transform_box.argtypes = [ctypes.c_void_p] * 5
+        L.idkhost_tlas_build.restype = None
+        L.idkhost_tlas_build.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32]
         L.idkhost_default_build_settings.restype = None
         L.idkhost_default_build_settings.argtypes = [ctypes.POINTER(IdkBlasBuildSettings)]
         _lib = L
@@ -231,6 +235,24 @@ class Scene:
                                         required_stack_size=b["required_stack_size"], sah=b["sah"]))
         # BVH.UpdateBlasStackSize (BVH.cs:559-567)
         self.blas_stack_size = max(1, int(self.blas_descs["RequiredStackSize"].max())) if len(self.blas_descs) else 1
+        return self
+
+    def build_tlas(self, use=True, search_radius=15):
+        """BVH.TlasBuild (SRC/Bvh/BVH.cs:278-298) + TLAS.Build (SRC/Bvh/TLAS.cs:28-141): world-space bounds of every BLAS
+        instance (Box.Transformed of the BLAS root by its ModelMatrix), serial PLOC; sets BVH.GpuUseTlas."""
+        n = len(self.blas_instances)
+        boxes = np.zeros((n, 6), np.float32)
+        L = lib()
+        for i, inst in enumerate(self.blas_instances):
+            root = self.blas_nodes[self.blas_descs[inst["BlasId"]]["NodeOffset"] + 1]
+            mn = np.ascontiguousarray(root["Min"], np.float32)
+            mx = np.ascontiguousarray(root["Max"], np.float32)
+            m = np.ascontiguousarray(self.mesh_transforms[inst["MeshTransformId"]]["ModelMatrix"], np.float32)
+            L.idkhost_transform_box(mn.ctypes.data, mx.ctypes.data, m.ctypes.data, boxes[i, :3].ctypes.data, boxes[i, 3:].ctypes.data)
+        self.tlas_nodes = np.zeros(max(2 * n - 1, 0), gt.GpuTlasNode)
+        if n:
+            L.idkhost_tlas_build(boxes.ctypes.data, n, self.tlas_nodes.ctypes.data, search_radius)
+        self.use_tlas = 1 if use else 0
         return self
 
     def add_light(self, position, color, radius):

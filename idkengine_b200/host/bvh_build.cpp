@@ -757,3 +757,130 @@ void idkhost_blas_copy(const IdkBlasBuild* b, GpuBlasNode* nodes, GpuBlasTriangl
 __attribute__((visibility("default"))) void idkhost_blas_free(IdkBlasBuild* b) { delete b; }
 
 } // extern "C"
+
+// ---------------------------------------------------------------- TLAS (Bvh/TLAS.cs:28-141, serial PLOC)
+namespace {
+
+static inline uint32_t insertTwoZeros(uint32_t v) {   // MyMath.InsertTwoZerosAfterEachBit
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+static inline uint32_t morton30(float x, float y, float z) {   // MyMath.GetMortonCode30
+    auto q = [](float f) { float s = f * 1024.0f; uint32_t u = s <= 0.0f ? 0u : (s >= 4294967040.0f ? 0xFFFFFFFFu : (uint32_t)s); return std::min(u, 1023u); };
+    return (insertTwoZeros(q(x)) << 2) | (insertTwoZeros(q(y)) << 1) | insertTwoZeros(q(z));
+}
+static inline Box tlasBox(const GpuTlasNode& n) { return {{n.Min[0], n.Min[1], n.Min[2]}, {n.Max[0], n.Max[1], n.Max[2]}}; }
+static inline void tlasSetBounds(GpuTlasNode& n, const Box& b) { for (int i = 0; i < 3; i++) { n.Min[i] = b.mn[i]; n.Max[i] = b.mx[i]; } }
+
+static int findBestMatch(const GpuTlasNode* nodes, int start, int end, int nodeIndex) {
+    float smallestArea = FLT_MAX;
+    int best = -1;
+    Box nodeBox = tlasBox(nodes[nodeIndex]);
+    for (int i = start; i < end; i++) {
+        if (i == nodeIndex) continue;
+        Box merged = nodeBox;
+        merged.grow(tlasBox(nodes[i]));
+        float area = merged.halfArea();
+        if (area < smallestArea) { smallestArea = area; best = i; }
+    }
+    return best;
+}
+
+} // namespace
+
+extern "C" {
+
+// Box.Transformed(localBounds, modelMatrix) (Shapes/Box.cs:166-175): 8 corners through the (column-vector) 3x4 model matrix.
+__attribute__((visibility("default")))
+void idkhost_transform_box(const float mn[3], const float mx[3], const float model3x4[12], float outMin[3], float outMax[3]) {
+    Box b = Box::empty();
+    for (int i = 0; i < 8; i++) {
+        float x = (i & 1) ? mx[0] : mn[0], y = (i & 2) ? mx[1] : mn[1], z = (i & 4) ? mx[2] : mn[2];
+        // OpenTK Vector4 * Matrix4 (row vector): x*Row0 + y*Row1 + z*Row2 + w*Row3; Row_k.c = model3x4[c][k]
+        V3 p;
+        p.x = x * model3x4[0] + y * model3x4[1] + z * model3x4[2] + 1.0f * model3x4[3];
+        p.y = x * model3x4[4] + y * model3x4[5] + z * model3x4[6] + 1.0f * model3x4[7];
+        p.z = x * model3x4[8] + y * model3x4[9] + z * model3x4[10] + 1.0f * model3x4[11];
+        b.grow(p);
+    }
+    for (int i = 0; i < 3; i++) { outMin[i] = b.mn[i]; outMax[i] = b.mx[i]; }
+}
+
+// TLAS.Build: boxes = primitiveCount x {min[3], max[3]} (world space), nodes = 2*primitiveCount-1 GpuTlasNode, root at 0.
+__attribute__((visibility("default")))
+void idkhost_tlas_build(const float* boxes, int32_t primitiveCount, GpuTlasNode* nodes, int32_t searchRadius) {
+    const int nodeCount = std::max(2 * primitiveCount - 1, 0);
+    if (nodeCount == 0) return;
+    std::vector<GpuTlasNode> temp(nodeCount);
+    memset(nodes, 0, sizeof(GpuTlasNode) * (size_t)nodeCount);
+    {
+        GpuTlasNode* leaves = temp.data() + (nodeCount - primitiveCount);
+        Box global = Box::empty();
+        for (int i = 0; i < primitiveCount; i++) {
+            Box b = {{boxes[6 * i], boxes[6 * i + 1], boxes[6 * i + 2]}, {boxes[6 * i + 3], boxes[6 * i + 4], boxes[6 * i + 5]}};
+            global.grow(b);
+            GpuTlasNode n = {};
+            tlasSetBounds(n, b);
+            n.IsLeafAndChildOrInstanceId = (1u << 31) | (uint32_t)i;
+            leaves[i] = n;
+        }
+        std::vector<std::pair<uint32_t, int>> keyed(primitiveCount);
+        for (int i = 0; i < primitiveCount; i++) {
+            const GpuTlasNode& n = leaves[i];
+            float c[3], m[3];
+            for (int a = 0; a < 3; a++) {
+                c[a] = (n.Max[a] + n.Min[a]) * 0.5f;
+                float t = global.mx[a] - global.mn[a];
+                m[a] = (c[a] - global.mn[a]) / t * (1.0f - 0.0f) + 0.0f;   // MyMath.MapToZeroOne / Remap
+                if (t == 0.0f) m[a] = 0.0f;
+            }
+            keyed[i] = {morton30(m[0], m[1], m[2]), i};
+        }
+        std::stable_sort(keyed.begin(), keyed.end(), [](const std::pair<uint32_t, int>& a, const std::pair<uint32_t, int>& b) { return a.first < b.first; });
+        for (int i = 0; i < primitiveCount; i++) nodes[nodeCount - primitiveCount + i] = leaves[keyed[i].second];
+    }
+    int activeRangeCount = primitiveCount, activeRangeEnd = nodeCount;
+    std::vector<int> pref(primitiveCount);
+    while (activeRangeCount > 1) {
+        const int activeRangeStart = activeRangeEnd - activeRangeCount;
+        for (int i = 0; i < activeRangeCount; i++) {
+            int a = activeRangeStart + i;
+            int s = std::max(a - searchRadius, activeRangeStart), e = std::min(a + searchRadius + 1, activeRangeEnd);
+            pref[i] = findBestMatch(nodes, s, e, a) - activeRangeStart;
+        }
+        int merged = 0;
+        for (int i = 0; i < activeRangeCount; i++) { int b = pref[i], c = pref[b]; if (i == c && i < b) merged += 2; }
+        const int unmerged = activeRangeCount - merged, newNodes = merged / 2;
+        int mergedHead = activeRangeEnd - merged;
+        const int newBegin = mergedHead - unmerged - newNodes;
+        int unmergedHead = newBegin;
+        for (int i = 0; i < activeRangeCount; i++) {
+            int b = pref[i], c = pref[b];
+            int aId = i + activeRangeStart;
+            if (i == c) {
+                if (i < b) {
+                    int bId = b + activeRangeStart;
+                    temp[mergedHead] = nodes[aId];
+                    temp[mergedHead + 1] = nodes[bId];
+                    Box mb = tlasBox(temp[mergedHead]);
+                    mb.grow(tlasBox(temp[mergedHead + 1]));
+                    GpuTlasNode nn = {};
+                    tlasSetBounds(nn, mb);
+                    nn.IsLeafAndChildOrInstanceId = (uint32_t)mergedHead;
+                    temp[unmergedHead++] = nn;
+                    mergedHead += 2;
+                }
+            } else {
+                temp[unmergedHead++] = nodes[aId];
+            }
+        }
+        memcpy(nodes + newBegin, temp.data() + newBegin, sizeof(GpuTlasNode) * (size_t)(activeRangeEnd - newBegin));
+        activeRangeCount -= merged / 2;
+        activeRangeEnd -= merged;
+    }
+}
+
+} // extern "C"

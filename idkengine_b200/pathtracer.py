@@ -68,8 +68,9 @@ class PathTracer:
         data = np.ascontiguousarray(data)
         self._check(self._lib.idkpt_update_range(self._ctx, which, first, len(data), data.ctypes.data), "idkpt_update_range")
 
-    def SetSky(self, color):
-        s = capi.sky_desc(color)
+    def SetSky(self, color, faces=None):
+        """Constant colour, or cubemap faces [6, N, N, 4] float32 (SkyBoxManager's samplerCube, UBO 5)."""
+        s = capi.sky_desc(color, faces)
         self._check(self._lib.idkpt_set_sky(self._ctx, ctypes.byref(s)), "idkpt_set_sky")
 
     def SetFrame(self, per_frame_data):

@@ -89,7 +89,8 @@ typedef enum IdkPtArrayId {
 
 /* Replaces SkyBoxManager's bindless samplerCube in UBO 5 (SkyBoxManager.cs:87):
  * either a constant colour or six rgba32f faces (+X,-X,+Y,-Y,+Z,-Z), FaceSize^2
- * texels each, sampled with nearest filtering. */
+ * texels each (row-major, GL face orientation), sampled with GL face selection +
+ * bilinear filtering inside the face (clamp to edge). */
 typedef struct IdkPtSkyDesc {
     float        Color[3];
     int32_t      FaceSize;       /* 0 => constant Color */

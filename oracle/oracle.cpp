@@ -120,6 +120,8 @@ static inline float det_exp(float x) {
 struct Scene {
     IdkPtSceneDesc d;
     float skyColor[3];
+    int skyFaceSize = 0;           // 0 = constant colour
+    const float* skyFaces[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // rgba32f, +X,-X,+Y,-Y,+Z,-Z
 };
 
 struct Ray { vec3 o, d; };
@@ -530,6 +532,28 @@ static inline vec3 CubemapFaceNormal(vec3 dir) {
     return {mx * -sgn(dir.x), my * -sgn(dir.y), mz * -sgn(dir.z)};
 }
 
+// texture(skyBoxUBO.Albedo, dir).rgb (FirstHit:227, NHit:208). Face selection and (s,t) per the OpenGL 4.6 spec table
+// 8.19 (major axis; ties x >= y >= z), then bilinear filtering inside the face with clamp-to-edge texel indices.
+struct Scene;
+static inline vec3 SampleSky(const float* const faces[6], int size, const float* constant, vec3 d) {
+    if (size == 0) return V(constant);
+    const float ax = fabsf(d.x), ay = fabsf(d.y), az = fabsf(d.z);
+    int face;
+    float sc, tc, ma;
+    if (ax >= ay && ax >= az) { face = d.x >= 0.0f ? 0 : 1; sc = d.x >= 0.0f ? -d.z : d.z; tc = -d.y; ma = ax; }
+    else if (ay >= az) { face = d.y >= 0.0f ? 2 : 3; sc = d.x; tc = d.y >= 0.0f ? d.z : -d.z; ma = ay; }
+    else { face = d.z >= 0.0f ? 4 : 5; sc = d.z >= 0.0f ? d.x : -d.x; tc = -d.y; ma = az; }
+    const float s = 0.5f * (sc / ma + 1.0f), t = 0.5f * (tc / ma + 1.0f);
+    const float px = s * (float)size - 0.5f, py = t * (float)size - 0.5f;
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float fx = px - fx0, fy = py - fy0;
+    auto cl = [&](int v) { return v < 0 ? 0 : (v > size - 1 ? size - 1 : v); };
+    const int x0 = cl((int)fx0), x1 = cl((int)fx0 + 1), y0 = cl((int)fy0), y1 = cl((int)fy0 + 1);
+    auto tx = [&](int x, int y) { const float* p = faces[face] + 4 * ((size_t)y * size + x); return V(p[0], p[1], p[2]); };
+    const vec3 a = mix(tx(x0, y0), tx(x1, y0), fx), b = mix(tx(x0, y1), tx(x1, y1), fx);
+    return mix(a, b, fy);
+}
+
 // ------------------------------------------------------------------ Surface / shading
 struct Surface {
     vec3 Albedo; float Alpha;
@@ -791,7 +815,7 @@ static bool ShadeTraceRay(const Scene& s, const Settings& st, Rng& rng, WRay& ra
         EncodeUnitVec(result.RayDirection, ray.PdX, ray.PdY);
         return true;
     } else {
-        vec3 albedo = V(s.skyColor);
+        vec3 albedo = SampleSky(s.skyFaces, s.skyFaceSize, s.skyColor, rayDir);
         if (firstHit) {
             aov.Albedo = albedo;
             aov.Normal = CubemapFaceNormal(rayDir);
@@ -936,7 +960,7 @@ ORACLE_API int oracle_path_trace(const IdkPtSceneDesc* scene, const IdkPtSkyDesc
                                  GpuWavefrontRay* raysOut, IdkPtStats* stats, int threads) {
     Scene s; s.d = *scene;
     for (int i = 0; i < 3; i++) s.skyColor[i] = sky ? sky->Color[i] : 0.0f;
-    if (sky && sky->FaceSize != 0) return -6;
+    if (sky && sky->FaceSize > 0) { s.skyFaceSize = sky->FaceSize; for (int i = 0; i < 6; i++) s.skyFaces[i] = sky->Faces[i]; }
     if (tileCount < 1) tileCount = 1;
     if (tileStripeHeight <= 0) tileStripeHeight = 8;
 

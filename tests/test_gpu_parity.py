@@ -134,6 +134,40 @@ def test_path_trace_lights_multi_blas_thin_lens(multi_blas):
     assert_same(*run_both(scene, cam, 160, 96, s, calls=2), aovs=True)
 
 
+def test_path_trace_cubemap_sky(cornell):
+    """SkyBoxManager's samplerCube on ray miss (FirstHit:227, NHit:208): six rgba32f faces instead of a constant."""
+    scene, cam = cornell
+    rng = np.random.RandomState(9)
+    faces = rng.uniform(0.0, 2.0, (6, 16, 16, 4)).astype(np.float32)
+    faces[2] *= 3.0          # bright +Y
+    s = capi.default_settings()
+    s.OutputAOVs = 1
+    g, o = run_both(scene, cam, 160, 120, s, calls=2, sky=faces)
+    assert_same(g, o, aovs=True)
+    g2, _ = run_both(scene, cam, 160, 120, s, calls=2, sky=(0.0, 0.0, 0.0))
+    assert not np.array_equal(g["result"], g2["result"])
+
+
+def test_tlas_traversal(multi_blas):
+    """USE_TLAS path (BVHIntersect.glsl:205-272): PLOC TLAS over the three BLAS instances, strict `<` child test, no
+    BLAS root test. Closest hits equal the no-TLAS instance loop except for exact-distance ties."""
+    scene, cam = scenes.multi_blas(threads=1)
+    scene.build_tlas()
+    assert len(scene.tlas_nodes) == 5 and scene.use_tlas == 1
+    rays = random_rays(12000, -2.5, 2.5, 21)
+    rays["Origin"][:, 1] = np.abs(rays["Origin"][:, 1]) + 0.2
+    with PathTracer(64, 64) as pt:
+        pt.SetScene(scene)
+        g, _ = pt.TraceRays(rays, trace_lights=True)
+    o = ol.trace_rays(scene, rays, trace_lights=True)
+    assert_hits_equal(g, o)
+    flat = ol.trace_rays(multi_blas[0], rays, trace_lights=True)
+    assert feq(g["T"], flat["T"])
+    s = capi.default_settings()
+    s.Gpu.DoTraceLights = 1
+    assert_same(*run_both(scene, cam, 128, 96, s, calls=2))
+
+
 def test_path_trace_debug_traversal(cornell):
     scene, cam = cornell
     s = capi.default_settings()
