@@ -61,7 +61,7 @@ struct IdkPtCtx {
     // launch configuration
     int traverseBlocks = 0, traverseBlocksStats = 0, shadeBlocks = 0, traceRaysBlocks = 0;
     int traverseVariant = 2;       // 2 = k_traverse2 (phase-scheduled warps), 1 = k_traverse (one ray per lane, reference loop)
-    TraverseTuning tune = {8, 8};
+    TraverseTuning tune = {12, 4};   // swept on B200 (profiles/r01b_tuning.txt)
     size_t stackBytes = 0;
 
     std::vector<cudaEvent_t> events;
