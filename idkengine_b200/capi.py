@@ -68,7 +68,8 @@ IDKPT_ARRAY_MESH_TRANSFORMS, IDKPT_ARRAY_MESHES, IDKPT_ARRAY_MATERIALS, IDKPT_AR
 EXPORTS = [
     "idkpt_create", "idkpt_destroy", "idkpt_last_error", "idkpt_set_scene", "idkpt_update_range", "idkpt_set_sky",
     "idkpt_resize", "idkpt_reset_accumulation", "idkpt_accumulated_samples", "idkpt_set_accumulated_samples",
-    "idkpt_compute", "idkpt_read_result", "idkpt_write_result", "idkpt_result_device_ptr", "idkpt_tile_rows",
+    "idkpt_compute", "idkpt_read_result", "idkpt_write_result", "idkpt_present_async", "idkpt_present_wait",
+    "idkpt_result_device_ptr", "idkpt_tile_rows",
     "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_abi_version",
 ]
 
@@ -172,6 +173,10 @@ def load(path=None):
     L.idkpt_read_result.argtypes = [c_vp, c_i32, c_vp, c_u64]
     L.idkpt_write_result.restype = c_i32
     L.idkpt_write_result.argtypes = [c_vp, c_i32, c_vp, c_u64]
+    L.idkpt_present_async.restype = c_i32
+    L.idkpt_present_async.argtypes = [c_vp, c_i32, c_vp, c_u64]
+    L.idkpt_present_wait.restype = c_i32
+    L.idkpt_present_wait.argtypes = [c_vp]
     L.idkpt_result_device_ptr.restype = c_i32
     L.idkpt_result_device_ptr.argtypes = [c_vp, c_i32, P(c_vp), P(c_u64)]
     L.idkpt_tile_rows.restype = c_i32

@@ -33,6 +33,8 @@ struct DeviceScene {
     int skyFaceSize;
     const float4* tlasNodes;      // 2 x float4 per GpuTlasNode, root at 0 (USE_TLAS path, BVHIntersect.glsl:205-272)
     int useTlas;
+    const float4* vtxFrame;       // device-private, 2 x float4 per vertex: decoded (normal.xyz, tangent.x) (tangent.yz, 0, 0)
+    const float4* surfRec;        // device-private, 5 x float4 per mesh: GetSurface + SurfaceApplyModificatons, see k_prepare_surfaces
 };
 
 #define IDK_TLAS_STACK_SIZE 24   // BVHIntersect.glsl:4
@@ -74,6 +76,47 @@ __global__ void k_prepare_triangles(const int4* __restrict__ tris, const float* 
     triRec[3 * (size_t)i + 0] = make_float4(p0.x, p0.y, p0.z, e1.x);
     triRec[3 * (size_t)i + 1] = make_float4(e1.y, e1.z, e2.x, e2.y);
     triRec[3 * (size_t)i + 2] = make_float4(e2.z, n.x, n.y, n.z);
+}
+
+// Scene upload: DecompressSR11G11B10 of every vertex normal / tangent (Compression.glsl:11-32), hoisted out of the
+// per-hit path (same fp32 operations, same bits).
+__global__ void k_prepare_vertices(const uint4* __restrict__ vertices, float4* __restrict__ vtxFrame, uint32_t count) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= count) return;
+    const uint4 v = vertices[i];
+    const f3 n = decompress_sr11g11b10(v.w), t = decompress_sr11g11b10(v.z);
+    vtxFrame[2 * (size_t)i] = make_float4(n.x, n.y, n.z, t.x);
+    vtxFrame[2 * (size_t)i + 1] = make_float4(t.y, t.z, 0.0f, 0.0f);
+}
+
+// Scene upload / mesh-material edits: with constant (1x1 white) textures the Surface of a hit depends only on its mesh:
+// GetSurface(material) (Surface.glsl:49-77) followed by SurfaceApplyModificatons(mesh) (Surface.glsl:85-96).
+//   [0] Albedo.xyz, Alpha   [1] Emissive.xyz, Metallic   [2] Absorbance.xyz, Roughness
+//   [3] Transmission, IOR, AlphaCutoff, NormalMapStrength   [4] flags (bit0 IsVolumetric, bit1 TintOnTransmissive)
+__global__ void k_prepare_surfaces(const GpuMesh* __restrict__ meshes, const GpuMaterial* __restrict__ materials,
+                                   float4* __restrict__ surfRec, uint32_t meshCount) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= meshCount) return;
+    const GpuMesh& mesh = meshes[i];
+    const GpuMaterial& mat = materials[mesh.MaterialId];
+    const uint32_t c = mat.BaseColorFactor;
+    const f3 albedo = mk3((float)(c & 255u) / 255.0f, (float)((c >> 8) & 255u) / 255.0f, (float)((c >> 16) & 255u) / 255.0f);
+    const float alpha = (float)((c >> 24) & 255u) / 255.0f;
+    f3 emissive = mk3(mat.EmissiveFactor[0], mat.EmissiveFactor[1], mat.EmissiveFactor[2]);
+    emissive = emissive * 1.0f + mesh.EmissiveBias * albedo;
+    const f3 ab = mk3(mat.Absorbance[0], mat.Absorbance[1], mat.Absorbance[2]) + mk3(mesh.AbsorbanceBias[0], mesh.AbsorbanceBias[1], mesh.AbsorbanceBias[2]);
+    const f3 absorbance = mk3(fmaxf(ab.x, 0.0f), fmaxf(ab.y, 0.0f), fmaxf(ab.z, 0.0f));
+    const float metallic = clamp1(mat.MetallicFactor + mesh.SpecularBias, 0.0f, 1.0f);
+    const float roughness = clamp1(mat.RoughnessFactor + mesh.RoughnessBias, 0.0f, 1.0f);
+    const float transmission = clamp1(mat.TransmissionFactor + mesh.TransmissionBias, 0.0f, 1.0f);
+    const float ior = fmaxf(mat.IOR + mesh.IORBias, 1.0f);
+    const uint32_t flags = (mat.IsVolumetric != 0 ? 1u : 0u) | (mesh.TintOnTransmissive != 0 ? 2u : 0u);
+    float4* o = surfRec + 5 * (size_t)i;
+    o[0] = make_float4(albedo.x, albedo.y, albedo.z, alpha);
+    o[1] = make_float4(emissive.x, emissive.y, emissive.z, metallic);
+    o[2] = make_float4(absorbance.x, absorbance.y, absorbance.z, roughness);
+    o[3] = make_float4(transmission, ior, mat.AlphaCutoff, mesh.NormalMapStrength);
+    o[4] = make_float4(__uint_as_float(flags), 0.0f, 0.0f, 0.0f);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -627,7 +670,7 @@ __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, uint32
     return ((unsigned long long)epoch << 34) | ((unsigned long long)flag << 32) | value;
 }
 
-__global__ void __launch_bounds__(IDK_BLOCK) k_shade(ShadeArgs a) {
+__global__ void __launch_bounds__(IDK_BLOCK, 3) k_shade(ShadeArgs a) {
     __shared__ uint32_t s_tile;
     __shared__ uint32_t s_warpCount[IDK_WARPS];
     __shared__ uint32_t s_base;
@@ -689,37 +732,34 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_shade(ShadeArgs a) {
                 if (!hitLight) {
                     sortingKey = hitTri;
                     const int4 tri = __ldg(sc.blasTris + hitTri);
-                    const uint4 v0 = __ldg(sc.vertices + tri.x), v1 = __ldg(sc.vertices + tri.y), v2 = __ldg(sc.vertices + tri.z);
-                    const float b0 = hv.x, b1 = hv.y, b2 = 1.0f - hv.x - hv.y;
-                    const f3 interpNormal = normalize3((decompress_sr11g11b10(v0.w) * b0 + decompress_sr11g11b10(v1.w) * b1) + decompress_sr11g11b10(v2.w) * b2);
-                    const f3 interpTangent = normalize3((decompress_sr11g11b10(v0.z) * b0 + decompress_sr11g11b10(v1.z) * b1) + decompress_sr11g11b10(v2.z) * b2);
+                    // independent gathers issued together: vertex frames, transform, per-mesh surface record, triangle normal
+                    const float4* vf = sc.vtxFrame;
+                    const float4 a0 = ldg4(vf + 2 * (size_t)tri.x), a1 = ldg4(vf + 2 * (size_t)tri.x + 1);
+                    const float4 c0 = ldg4(vf + 2 * (size_t)tri.y), c1 = ldg4(vf + 2 * (size_t)tri.y + 1);
+                    const float4 e0 = ldg4(vf + 2 * (size_t)tri.z), e1 = ldg4(vf + 2 * (size_t)tri.z + 1);
                     const float4* xf = sc.xforms + 9 * (size_t)hitXf + 3;
                     const float4 r0 = ldg4(xf), r1 = ldg4(xf + 1), r2 = ldg4(xf + 2);
-                    const GpuMesh& mesh = sc.meshes[tri.w];
-                    const GpuMaterial& mat = sc.materials[mesh.MaterialId];
+                    const float4* sr = sc.surfRec + 5 * (size_t)tri.w;
+                    const float4 s0 = ldg4(sr), s1 = ldg4(sr + 1), s2 = ldg4(sr + 2), s3 = ldg4(sr + 3), s4 = ldg4(sr + 4);
+                    const float b0 = hv.x, b1 = hv.y, b2 = 1.0f - hv.x - hv.y;
+                    const f3 interpNormal = normalize3((mk3(a0.x, a0.y, a0.z) * b0 + mk3(c0.x, c0.y, c0.z) * b1) + mk3(e0.x, e0.y, e0.z) * b2);
+                    const f3 interpTangent = normalize3((mk3(a0.w, a1.x, a1.y) * b0 + mk3(c0.w, c1.x, c1.y) * b1) + mk3(e0.w, e1.x, e1.y) * b2);
+                    const float normalMapStrength = s3.w;
 
-                    // GetSurface with 1x1 white textures (Surface.glsl:49-77)
-                    const uint32_t c = mat.BaseColorFactor;
-                    s.Albedo = mk3((float)(c & 255u) / 255.0f, (float)((c >> 8) & 255u) / 255.0f, (float)((c >> 16) & 255u) / 255.0f);
-                    s.Alpha = (float)((c >> 24) & 255u) / 255.0f;
+                    // GetSurface (1x1 white textures, Surface.glsl:49-77) + SurfaceApplyModificatons (Surface.glsl:85-96),
+                    // precomputed per mesh at upload (k_prepare_surfaces)
+                    s.Albedo = mk3(s0.x, s0.y, s0.z);
+                    s.Alpha = s0.w;
                     s.Normal = mk3(1.0f, 1.0f, 0.0f);
-                    s.Emissive = mk3(mat.EmissiveFactor[0], mat.EmissiveFactor[1], mat.EmissiveFactor[2]);
-                    s.Absorbance = mk3(mat.Absorbance[0], mat.Absorbance[1], mat.Absorbance[2]);
-                    s.Metallic = mat.MetallicFactor;
-                    s.Roughness = mat.RoughnessFactor;
-                    s.Transmission = mat.TransmissionFactor;
-                    s.IOR = mat.IOR;
-                    s.AlphaCutoff = mat.AlphaCutoff;
-                    s.IsVolumetric = mat.IsVolumetric != 0;
-                    // SurfaceApplyModificatons (Surface.glsl:85-96)
-                    s.Emissive = s.Emissive * 1.0f + mesh.EmissiveBias * s.Albedo;
-                    const f3 ab = s.Absorbance + mk3(mesh.AbsorbanceBias[0], mesh.AbsorbanceBias[1], mesh.AbsorbanceBias[2]);
-                    s.Absorbance = mk3(fmaxf(ab.x, 0.0f), fmaxf(ab.y, 0.0f), fmaxf(ab.z, 0.0f));
-                    s.Metallic = clamp1(s.Metallic + mesh.SpecularBias, 0.0f, 1.0f);
-                    s.Roughness = clamp1(s.Roughness + mesh.RoughnessBias, 0.0f, 1.0f);
-                    s.Transmission = clamp1(s.Transmission + mesh.TransmissionBias, 0.0f, 1.0f);
-                    s.IOR = fmaxf(s.IOR + mesh.IORBias, 1.0f);
-                    s.TintOnTransmissive = mesh.TintOnTransmissive != 0;
+                    s.Emissive = mk3(s1.x, s1.y, s1.z);
+                    s.Metallic = s1.w;
+                    s.Absorbance = mk3(s2.x, s2.y, s2.z);
+                    s.Roughness = s2.w;
+                    s.Transmission = s3.x;
+                    s.IOR = s3.y;
+                    s.AlphaCutoff = s3.z;
+                    s.IsVolumetric = (__float_as_uint(s4.x) & 1u) != 0;
+                    s.TintOnTransmissive = (__float_as_uint(s4.x) & 2u) != 0;
 
                     const float alphaCutoff = (s.AlphaCutoff == 2.0f) ? rnd01(rng) : s.AlphaCutoff;
                     if (s.Alpha < alphaCutoff) {
@@ -732,7 +772,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_shade(ShadeArgs a) {
                         const f3 T = normalize3(worldTangent);
                         const f3 B = normalize3(cross3(N, T));
                         const f3 tbnN = (T * s.Normal.x + B * s.Normal.y) + N * s.Normal.z;
-                        s.Normal = normalize3(mix3(worldNormal, tbnN, mesh.NormalMapStrength));
+                        s.Normal = normalize3(mix3(worldNormal, tbnN, normalMapStrength));
                         const float4 tr = ldg4(sc.triRec + 3 * (size_t)hitTri + 2);
                         geometricNormal = normalize3(mk3(tr.y, tr.z, tr.w));   // GetTriangleNormal
                         geometricNormal = normalize3(xform_normal(r0, r1, r2, geometricNormal));
@@ -815,8 +855,8 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_shade(ShadeArgs a) {
                         const bool gltfWantsTint = m.IsVolumetric || !fromInside;
                         bsdf = (gltfWantsTint && m.TintOnTransmissive) ? m.Albedo : mk3(1.0f, 1.0f, 1.0f);
                     }
-                    const float pdf = fmaxf(1.0f, 0.0001f);
-                    thr = thr * (bsdf / pdf);
+                    // result.Pdf = max(1.0, 0.0001) = 1.0 in every branch; bsdf / 1.0f == bsdf exactly
+                    thr = thr * bsdf;
 
                     if (a.outputAovs) {
                         // GetSurfaceVariance uses the un-remapped surface (FirstHit:197-203)

@@ -40,7 +40,7 @@ struct IdkPtCtx {
     bool haveScene = false;
     DeviceScene sc = {};
     IdkPtSceneDesc counts = {};    // element counts only (pointers unused)
-    DevBuf nodes, triRec, blasTris, positions, descs, instances, xforms, meshes, materials, vertices, lights, tlas;
+    DevBuf nodes, triRec, blasTris, positions, descs, instances, xforms, meshes, materials, vertices, lights, tlas, vtxFrame, surfRec;
     float sky[3] = {0.0f, 0.0f, 0.0f};
     DevBuf skyFaces;
     int skyFaceSize = 0;
@@ -65,6 +65,12 @@ struct IdkPtCtx {
     size_t stackBytes = 0;
 
     std::vector<cudaEvent_t> events;
+
+    // asynchronous presentation (device snapshot + D2H on a second stream, overlapping the next Compute)
+    cudaStream_t copyStream = nullptr;
+    cudaEvent_t snapDone = nullptr, copyDone = nullptr;
+    DevBuf presentSnap;
+    bool copyPending = false;
 };
 
 #define CK(call)                                                                                   \
@@ -228,13 +234,17 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->nodes, &ctx->triRec, &ctx->blasTris, &ctx->positions, &ctx->descs, &ctx->instances, &ctx->xforms,
-                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->state[0], &ctx->state[1], &ctx->aov[0],
+                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->vtxFrame, &ctx->surfRec, &ctx->state[0], &ctx->state[1], &ctx->aov[0],
                      &ctx->aov[1], &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
                      &ctx->aovNormalFinal, &ctx->exportRays, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
                      &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->perm, &ctx->countLog, &ctx->skyFaces};
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ctx->sortScratch);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
+    if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
+    if (ctx->snapDone) cudaEventDestroy(ctx->snapDone);
+    if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
+    release(ctx->presentSnap);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -301,6 +311,17 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
         if ((uint64_t)(uint32_t)t.X >= lim || (uint64_t)(uint32_t)t.Y >= lim || (uint64_t)(uint32_t)t.Z >= lim || t.MeshId < 0 || (uint64_t)t.MeshId >= s->MeshCount)
             return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuBlasTriangle index out of range");
     }
+    CK(ensure(ctx->vtxFrame, std::max<size_t>(s->VertexCount, 1) * 32));
+    CK(ensure(ctx->surfRec, std::max<size_t>(s->MeshCount, 1) * 80));
+    if (s->VertexCount) {
+        const uint32_t nv = (uint32_t)s->VertexCount;
+        k_prepare_vertices<<<(nv + 255) / 256, 256, 0, ctx->stream>>>((const uint4*)ctx->vertices.p, (float4*)ctx->vtxFrame.p, nv);
+    }
+    if (s->MeshCount) {
+        const uint32_t nm = (uint32_t)s->MeshCount;
+        k_prepare_surfaces<<<(nm + 255) / 256, 256, 0, ctx->stream>>>((const GpuMesh*)ctx->meshes.p, (const GpuMaterial*)ctx->materials.p, (float4*)ctx->surfRec.p, nm);
+    }
+    CK(cudaGetLastError());
     if (s->BlasTriangleCount) {
         const uint32_t n = (uint32_t)s->BlasTriangleCount;
         k_prepare_triangles<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const int4*)ctx->blasTris.p, (const float*)ctx->positions.p, (float4*)ctx->triRec.p, n);
@@ -326,6 +347,8 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     sc.stackSize = std::max(1, s->BlasStackSize);
     sc.tlasNodes = (const float4*)ctx->tlas.p;
     sc.useTlas = s->UseTlas ? 1 : 0;
+    sc.vtxFrame = (const float4*)ctx->vtxFrame.p;
+    sc.surfRec = (const float4*)ctx->surfRec.p;
     ctx->counts = *s;
     if ((rc = configure_launches(ctx))) return rc;
     CK(cudaStreamSynchronize(ctx->stream));
@@ -355,7 +378,18 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
             if (m[i].MaterialId < 0 || (uint64_t)m[i].MaterialId >= ctx->counts.MaterialCount)
                 return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: GpuMesh.MaterialId out of range");
     }
+    if (which == IDKPT_ARRAY_MATERIALS) {
+        const GpuMaterial* m = (const GpuMaterial*)data;
+        for (uint64_t i = 0; i < count; i++)
+            if (m[i].BaseColorTexture || m[i].MetallicRoughnessTexture || m[i].NormalTexture || m[i].EmissiveTexture || m[i].TransmissionTexture)
+                return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_update_range: non-null texture handles are not supported yet");
+    }
     CK(cudaMemcpyAsync((char*)b->p + first * elem, data, count * elem, cudaMemcpyHostToDevice, ctx->stream));
+    if ((which == IDKPT_ARRAY_MESHES || which == IDKPT_ARRAY_MATERIALS) && ctx->counts.MeshCount) {
+        const uint32_t nm = (uint32_t)ctx->counts.MeshCount;   // refresh the per-mesh surface records
+        k_prepare_surfaces<<<(nm + 255) / 256, 256, 0, ctx->stream>>>((const GpuMesh*)ctx->meshes.p, (const GpuMaterial*)ctx->materials.p, (float4*)ctx->surfRec.p, nm);
+        CK(cudaGetLastError());
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->accumulatedSamples = 0;
     return IDKPT_OK;
@@ -386,6 +420,7 @@ IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height) {
     if (width <= 0 || height <= 0 || width > 16384 || height > 16384) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_resize: invalid size");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->copyPending) { CK(cudaEventSynchronize(ctx->copyDone)); ctx->copyPending = false; }
     ctx->width = width;
     ctx->height = height;
     compute_tile_rows(ctx);
@@ -641,6 +676,48 @@ static int image_copy(IdkPtCtx* ctx, IdkPtImage which, void* host, uint64_t byte
 
 IDKPT_API int idkpt_read_result(IdkPtCtx* ctx, IdkPtImage which, void* dst, uint64_t bytes) { return image_copy(ctx, which, dst, bytes, true); }
 IDKPT_API int idkpt_write_result(IdkPtCtx* ctx, IdkPtImage which, const void* src, uint64_t bytes) { return image_copy(ctx, which, (void*)src, bytes, false); }
+
+// Present without stalling the renderer: snapshot the image on the device (ordered after the Compute that produced it)
+// and copy the snapshot to (ideally pinned) host memory on a second stream, so the transfer overlaps the next Compute.
+IDKPT_API int idkpt_present_async(IdkPtCtx* ctx, IdkPtImage which, void* dstHost, uint64_t bytes) {
+    if (!ctx || !dstHost) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: null argument");
+    if ((int)which < 0 || (int)which > 2) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: unknown image");
+    if (bytes < (uint64_t)ctx->width * ctx->height * 16) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: buffer smaller than width*height*16");
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->copyStream) {
+        CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->snapDone, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming));
+    }
+    const size_t n = (size_t)ctx->nLocal * 16;
+    CK(ensure(ctx->presentSnap, std::max<size_t>(n, 16)));
+    if (ctx->copyPending) CK(cudaStreamWaitEvent(ctx->stream, ctx->copyDone, 0));   // previous transfer still reads the snapshot
+    CK(cudaMemcpyAsync(ctx->presentSnap.p, ctx->images[which].p, n, cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaEventRecord(ctx->snapDone, ctx->stream));
+    CK(cudaStreamWaitEvent(ctx->copyStream, ctx->snapDone, 0));
+    const size_t rowBytes = (size_t)ctx->width * 16;
+    size_t i = 0;
+    while (i < ctx->rows.size()) {
+        size_t j = i;
+        while (j + 1 < ctx->rows.size() && ctx->rows[j + 1] == ctx->rows[j] + 1) j++;
+        CK(cudaMemcpyAsync((char*)dstHost + (size_t)ctx->rows[i] * rowBytes, (char*)ctx->presentSnap.p + i * rowBytes, (j - i + 1) * rowBytes,
+                           cudaMemcpyDeviceToHost, ctx->copyStream));
+        i = j + 1;
+    }
+    CK(cudaEventRecord(ctx->copyDone, ctx->copyStream));
+    ctx->copyPending = true;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_present_wait(IdkPtCtx* ctx) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    if (ctx->copyPending) {
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaEventSynchronize(ctx->copyDone));
+        ctx->copyPending = false;
+    }
+    return IDKPT_OK;
+}
 
 IDKPT_API int idkpt_result_device_ptr(IdkPtCtx* ctx, IdkPtImage which, void** devPtr, uint64_t* bytes) {
     if (!ctx || !devPtr || (int)which < 0 || (int)which > 2) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_result_device_ptr: invalid argument");

@@ -127,6 +127,14 @@ class PathTracer:
         if accumulated is not None:
             self._check(self._lib.idkpt_set_accumulated_samples(self._ctx, accumulated), "idkpt_set_accumulated_samples")
 
+    def PresentAsync(self, host_ptr, nbytes, which=capi.IDKPT_IMAGE_RESULT):
+        """Start copying the image of the last Compute() into host memory (pinned for full overlap) on a second stream;
+        the next Compute() overlaps the transfer. PresentWait() blocks until it has landed."""
+        self._check(self._lib.idkpt_present_async(self._ctx, which, host_ptr, nbytes), "idkpt_present_async")
+
+    def PresentWait(self):
+        self._check(self._lib.idkpt_present_wait(self._ctx), "idkpt_present_wait")
+
     def ResultDevicePtr(self, which=capi.IDKPT_IMAGE_RESULT):
         p, n = ctypes.c_void_p(), ctypes.c_uint64()
         self._check(self._lib.idkpt_result_device_ptr(self._ctx, which, ctypes.byref(p), ctypes.byref(n)), "idkpt_result_device_ptr")

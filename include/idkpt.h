@@ -173,6 +173,12 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
 IDKPT_API int idkpt_read_result(IdkPtCtx* ctx, IdkPtImage which, void* dst_rgba32f, uint64_t bytes);
 IDKPT_API int idkpt_write_result(IdkPtCtx* ctx, IdkPtImage which, const void* src_rgba32f, uint64_t bytes);
 
+/* Asynchronous presentation: snapshot the image (ordered after the Compute that produced it) and copy it to host memory
+ * (pinned for full overlap) on a second stream while the next idkpt_compute runs; idkpt_present_wait blocks until the
+ * most recent transfer has landed. The GL-free analogue of handing Result to the presenter each frame. */
+IDKPT_API int idkpt_present_async(IdkPtCtx* ctx, IdkPtImage which, void* dst_rgba32f_host, uint64_t bytes);
+IDKPT_API int idkpt_present_wait(IdkPtCtx* ctx);
+
 /* Device-side access for zero-copy hand-over (GL interop / NCCL gather):
  * pointer to this tile's compact rgba32f rows (TileRowCount*Width float4). */
 IDKPT_API int idkpt_result_device_ptr(IdkPtCtx* ctx, IdkPtImage which, void** dev_ptr, uint64_t* bytes);

@@ -152,3 +152,42 @@ def test_real_sponza_builds_like_the_readme_says():
     frame = scenes.camera_frame(cam, 96, 54)
     rays = ol.primary_rays(frame, 96, 54)
     _compare_to_brute_force(scene, rays)
+
+
+def test_tlas_ploc_structure_and_equivalence(multi_blas):
+    """TLAS.Build mirror (SRC/Bvh/TLAS.cs:28-141): 2n-1 nodes, root at 0, children adjacent, every instance in exactly
+    one leaf, parents bound their children; the TLAS walk finds the same closest distances as the instance loop."""
+    scene, cam = scenes.multi_blas(threads=1)
+    scene.build_tlas()
+    t = scene.tlas_nodes
+    n = len(scene.blas_instances)
+    assert len(t) == 2 * n - 1
+    leaf = (t["IsLeafAndChildOrInstanceId"] >> 31) == 1
+    ids = t["IsLeafAndChildOrInstanceId"] & 0x7FFFFFFF
+    assert sorted(ids[leaf].tolist()) == list(range(n)) and not leaf[0]
+    for i in np.nonzero(~leaf)[0]:
+        c = ids[i]
+        assert i < c < len(t) - 1
+        assert np.all(t["Min"][i] <= np.minimum(t["Min"][c], t["Min"][c + 1]) + 1e-6)
+        assert np.all(t["Max"][i] >= np.maximum(t["Max"][c], t["Max"][c + 1]) - 1e-6)
+    rng = np.random.RandomState(2)
+    o = rng.uniform(-2.5, 2.5, (3000, 3)).astype(np.float32)
+    o[:, 1] = np.abs(o[:, 1]) + 0.2
+    d = rng.normal(size=(3000, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rays = ol.make_rays(o, d)
+    a = ol.trace_rays(multi_blas[0], rays)
+    b = ol.trace_rays(scene, rays)
+    assert np.array_equal(a["T"], b["T"])
+    # a bigger forest of instances: 40 copies of a small BLAS scattered around
+    from idkengine_b200.host import Scene, Model, trs_matrix
+    pos, idx = scenes.uv_sphere([0, 0, 0], 0.5, 8, 12)
+    sc = Scene()
+    for k in range(40):
+        sc.add(Model(pos, idx, model_matrix=trs_matrix(0.5 + 0.02 * k, 7.0 * k, (rng.uniform(-6, 6), rng.uniform(0, 3), rng.uniform(-6, 6))), name=f"s{k}"), threads=1)
+    flat = ol.trace_rays(sc, rays)
+    sc.build_tlas()
+    assert len(sc.tlas_nodes) == 79
+    tl = ol.trace_rays(sc, rays)
+    assert np.array_equal(flat["T"], tl["T"])
+    assert np.array_equal(flat["TriangleId"], tl["TriangleId"])

@@ -263,6 +263,58 @@ def test_errors(cornell):
         PathTracer(32, 32, device=99)
 
 
+def test_update_range_materials_meshes_transforms(multi_blas):
+    """Dirty-range edits (ModelManager.cs:236-261): material / mesh / transform changes reach the kernels."""
+    scene, cam = scenes.multi_blas(threads=1)
+    s = capi.default_settings()
+    s.RayDepth = 4
+    frame = scenes.camera_frame(cam, 96, 64)
+    with PathTracer(96, 64, s) as pt:
+        pt.SetScene(scene)
+        pt.SetFrame(frame)
+        pt.Compute()
+        scene.materials["BaseColorFactor"][2] = 0xFF2040F0
+        scene.materials["MetallicFactor"][2] = 0.9
+        pt.UpdateRange(capi.IDKPT_ARRAY_MATERIALS, 2, scene.materials[2:3])
+        scene.meshes["EmissiveBias"][0] = 0.7
+        scene.meshes["RoughnessBias"][2] = -0.4
+        pt.UpdateRange(capi.IDKPT_ARRAY_MESHES, 0, scene.meshes)
+        from idkengine_b200.host import mesh_transform, trs_matrix
+        scene.mesh_transforms[1] = mesh_transform(trs_matrix(0.9, 30.0, (-1.0, 0.9, 0.2)))[0]
+        pt.UpdateRange(capi.IDKPT_ARRAY_MESH_TRANSFORMS, 1, scene.mesh_transforms[1:2])
+        assert pt.AccumulatedSamples == 0
+        pt.Compute()
+        img = pt.Result
+    o = ol.path_trace(scene, frame, s, 96, 64, sky=(0, 0, 0))
+    assert feq(img, o.result)
+
+
+def test_present_async_matches_read_result(cornell):
+    import torch
+    scene, cam = cornell
+    w, h = 160, 96
+    bufs = [torch.zeros((h, w, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
+    with PathTracer(w, h) as pt:
+        pt.SetScene(scene)
+        pt.SetFrame(scenes.camera_frame(cam, w, h))
+        imgs = []
+        for k in range(4):
+            pt.Compute()
+            pt.PresentAsync(bufs[k & 1].data_ptr(), bufs[k & 1].numel() * 4)
+            if k >= 1:
+                pass
+            imgs.append(pt.Result)            # synchronous read of the same frame
+            pt.PresentWait()
+            assert np.array_equal(bufs[k & 1].numpy(), imgs[-1])
+        # pipelined use: present k overlaps compute k+1
+        pt.ResetAccumulation()
+        for k in range(4):
+            pt.Compute()
+            pt.PresentAsync(bufs[k & 1].data_ptr(), bufs[k & 1].numel() * 4)
+        pt.PresentWait()
+        assert np.array_equal(bufs[1].numpy(), imgs[3])
+
+
 def test_resize_and_snapshot_restore(cornell):
     scene, cam = cornell
     s = capi.default_settings()
