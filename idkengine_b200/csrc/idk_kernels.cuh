@@ -642,24 +642,19 @@ __device__ __forceinline__ f3 sample_sky(const DeviceScene& sc, f3 d) {
 struct ShadeArgs {
     DeviceScene sc;
     FrameParams f;
-    const PathState* stateIn;      // by perm[gid] / gid
-    PathState* stateOut;           // by new slot
-    const float4* aovIn;           // 2 x float4 per slot (by perm[gid] / gid)
-    float4* aovOut;
-    const uint32_t* perm;          // may be null
-    const HitRec* hits;            // by gid
+    PathState* state;              // pixel-indexed, updated in place (the reference's Rays[rayIndex], SSBO 30)
+    float4* aov;                   // 2 x float4 per pixel, in place (SSBO 31), AOVs only
+    const uint32_t* alive;         // alive list of this bounce: slot -> tile pixel; null = identity (first hit)
+    const HitRec* hits;            // by slot
     const uint32_t* hitXform;
-    const float* debugCost;        // by gid (debug traversal only)
+    const float* debugCost;        // by slot (debug traversal only)
     const uint32_t* count;         // alive count in
-    uint32_t* countOut;            // alive count out (pre-zeroed)
-    uint32_t* ticket;              // tile ticket (pre-zeroed)
-    unsigned long long* tileStatus;// decoupled look-back status words, tagged with epoch
-    uint32_t epoch;
-    uint32_t* keysOut;             // sort key per new slot (ray sorting only), may be null
+    uint32_t* survivors;           // by slot: tile pixel of a surviving ray, ~0u otherwise (input of k_compact)
+    uint32_t* keysTmp;             // by slot: sort key of a surviving ray (ray sorting only), may be null
     float4* radiance;              // per tile pixel: final radiance (w = traversal cost)
     float4* aovAlbedoFinal;        // per tile pixel (AOVs only)
     float4* aovNormalFinal;
-    GpuWavefrontRay* exportRays;   // per tile pixel, reference layout (debug export), may be null
+    int exportState;               // debug export: terminated paths also write their final state back
     int firstHit;
     int lastBounce;                // survivors are final: no compaction
     int outputAovs;
@@ -670,39 +665,29 @@ __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, uint32
     return ((unsigned long long)epoch << 34) | ((unsigned long long)flag << 32) | value;
 }
 
+// One thread per alive ray, no block-level cooperation: every warp runs at its own pace (the ordered compaction of
+// the reference's atomic alive list is a separate, uniform-cost pass over 4-byte entries: k_compact).
 __global__ void __launch_bounds__(IDK_BLOCK, 3) k_shade(ShadeArgs a) {
-    __shared__ uint32_t s_tile;
-    __shared__ uint32_t s_warpCount[IDK_WARPS];
-    __shared__ uint32_t s_base;
     const uint32_t count = *a.count;
-    const uint32_t numTiles = (count + IDK_BLOCK - 1) / IDK_BLOCK;
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const DeviceScene& sc = a.sc;
     const FrameParams& f = a.f;
 
-    for (;;) {
-        __syncthreads();
-        if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
-        __syncthreads();
-        const uint32_t tile = s_tile;
-        if (tile >= numTiles) break;
-        const uint32_t gid = tile * IDK_BLOCK + threadIdx.x;
+    for (uint32_t gid = blockIdx.x * blockDim.x + threadIdx.x; gid < count; gid += gridDim.x * blockDim.x) {
         bool survive = false;
         PathState st;
         float4 aov0 = make_float4(0.0f, 0.0f, 0.0f, 1.0f), aov1 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         uint32_t sortingKey = 0;
-
-        if (gid < count) {
-            const uint32_t src = a.perm ? a.perm[gid] : gid;
+        const uint32_t src = a.alive ? a.alive[gid] : gid;
+        {
             {
-                const float4* sp = reinterpret_cast<const float4*>(a.stateIn + src);
+                const float4* sp = reinterpret_cast<const float4*>(a.state + src);
                 float4 v0 = sp[0], v1 = sp[1], v2 = sp[2], v3 = sp[3];
                 st.ox = v0.x; st.oy = v0.y; st.oz = v0.z; st.prevIor = v0.w;
                 st.pdx = v1.x; st.pdy = v1.y; st.pix = __float_as_uint(v1.z); st.reseed = __float_as_uint(v1.w);
                 st.tx = v2.x; st.ty = v2.y; st.tz = v2.z; st.rng = __float_as_uint(v2.w);
                 st.rx = v3.x; st.ry = v3.y; st.rz = v3.z; st.pad = 0;
             }
-            if (a.outputAovs && !a.firstHit) { aov0 = a.aovIn[2 * (size_t)src]; aov1 = a.aovIn[2 * (size_t)src + 1]; }
+            if (a.outputAovs && !a.firstHit) { aov0 = a.aov[2 * (size_t)src]; aov1 = a.aov[2 * (size_t)src + 1]; }
             uint32_t rng = a.firstHit ? st.rng : (gid * 4096u + f.accumulatedSamples);
             const uint32_t reseed = a.firstHit ? st.reseed : gid;   // gl_GlobalInvocationID.y*4096 + .x
 
@@ -911,23 +896,76 @@ __global__ void __launch_bounds__(IDK_BLOCK, 3) k_shade(ShadeArgs a) {
 
             if (!survive || a.lastBounce) {
                 // path is final for this sample: hand its radiance (and AOVs) to the accumulate kernel
-                a.radiance[st.pix] = make_float4(st.rx, st.ry, st.rz, st.prevIor);
-                if (a.outputAovs) { a.aovAlbedoFinal[st.pix] = aov0; a.aovNormalFinal[st.pix] = aov1; }
-                if (a.exportRays) {
-                    GpuWavefrontRay w;
-                    w.Origin[0] = st.ox; w.Origin[1] = st.oy; w.Origin[2] = st.oz; w.PreviousIOROrTraverseCost = st.prevIor;
-                    w.Throughput[0] = st.tx; w.Throughput[1] = st.ty; w.Throughput[2] = st.tz; w.PackedDirectionX = st.pdx;
-                    w.Radiance[0] = st.rx; w.Radiance[1] = st.ry; w.Radiance[2] = st.rz; w.PackedDirectionY = st.pdy;
-                    a.exportRays[st.pix] = w;
-                }
+                a.radiance[src] = make_float4(st.rx, st.ry, st.rz, st.prevIor);
+                if (a.outputAovs) { a.aovAlbedoFinal[src] = aov0; a.aovNormalFinal[src] = aov1; }
+            }
+            if ((survive && !a.lastBounce) || a.exportState) {
+                // wavefrontRaySSBO.Rays[rayIndex] = wavefrontRay (FirstHit:84, NHit:63), in place
+                float4* op = reinterpret_cast<float4*>(a.state + src);
+                op[0] = make_float4(st.ox, st.oy, st.oz, st.prevIor);
+                op[1] = make_float4(st.pdx, st.pdy, __uint_as_float(src), 0.0f);
+                op[2] = make_float4(st.tx, st.ty, st.tz, 0.0f);
+                op[3] = make_float4(st.rx, st.ry, st.rz, 0.0f);
+                if (a.outputAovs) { a.aov[2 * (size_t)src] = aov0; a.aov[2 * (size_t)src + 1] = aov1; }
+            }
+            if (!a.lastBounce) {
+                a.survivors[gid] = survive ? src : ~0u;
+                if (a.keysTmp) a.keysTmp[gid] = sortingKey & 0x1FFFFFu;
             }
         }
-        if (a.lastBounce) continue;
+    }
+}
 
-        // ---- ordered compaction: block scan + decoupled look-back across tiles (ascending slot order)
-        const uint32_t ballot = __ballot_sync(0xffffffffu, survive);
-        const uint32_t rankInWarp = __popc(ballot & ((1u << lane) - 1u));
-        if (lane == 0) s_warpCount[warp] = __popc(ballot);
+// ------------------------------------------------------------------------------------------------
+// Ordered stream compaction of the survivor list: the canonical (ascending slot) outcome of the reference's
+// `index = atomicAdd(Counts[1 - pingPong], 1); AliveRayIndices[index] = rayIndex` (FirstHit:89-97, NHit:69-77).
+// Single pass, decoupled look-back over tiles of IDK_BLOCK x IDK_COMPACT_ITEMS entries; every tile costs the same,
+// so the look-back never waits long (unlike doing it inside the shading kernel).
+#define IDK_COMPACT_ITEMS 8
+struct CompactArgs {
+    const uint32_t* survivors;     // by slot: pixel or ~0u
+    const uint32_t* keysTmp;       // by slot, may be null
+    const uint32_t* count;
+    uint32_t* aliveOut;
+    uint32_t* keysOut;             // may be null
+    uint32_t* countOut;
+    uint32_t* ticket;
+    unsigned long long* tileStatus;
+    uint32_t epoch;
+};
+
+__global__ void __launch_bounds__(IDK_BLOCK) k_compact(CompactArgs a) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t s_warpCount[IDK_WARPS];
+    __shared__ uint32_t s_base;
+    const uint32_t count = *a.count;
+    const uint32_t tileSize = IDK_BLOCK * IDK_COMPACT_ITEMS;
+    const uint32_t numTiles = (count + tileSize - 1) / tileSize;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= numTiles) break;
+        // each thread owns IDK_COMPACT_ITEMS consecutive slots (keeps the order trivially stable)
+        const uint32_t first = tile * tileSize + threadIdx.x * IDK_COMPACT_ITEMS;
+        uint32_t v[IDK_COMPACT_ITEMS];
+        uint32_t mine = 0;
+#pragma unroll
+        for (int i = 0; i < IDK_COMPACT_ITEMS; i++) {
+            const uint32_t s = first + i;
+            v[i] = s < count ? a.survivors[s] : ~0u;
+            mine += v[i] != ~0u ? 1u : 0u;
+        }
+        // warp exclusive scan of per-thread counts
+        uint32_t incl = mine;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, off);
+            if ((int)lane >= off) incl += n;
+        }
+        if (lane == 31) s_warpCount[warp] = incl;
         __syncthreads();
         uint32_t warpOffset = 0, blockTotal = 0;
 #pragma unroll
@@ -956,15 +994,14 @@ __global__ void __launch_bounds__(IDK_BLOCK, 3) k_shade(ShadeArgs a) {
             s_base = exclusive;
         }
         __syncthreads();
-        if (survive) {
-            const uint32_t dst = s_base + warpOffset + rankInWarp;
-            float4* op = reinterpret_cast<float4*>(a.stateOut + dst);
-            op[0] = make_float4(st.ox, st.oy, st.oz, st.prevIor);
-            op[1] = make_float4(st.pdx, st.pdy, __uint_as_float(st.pix), 0.0f);
-            op[2] = make_float4(st.tx, st.ty, st.tz, 0.0f);
-            op[3] = make_float4(st.rx, st.ry, st.rz, 0.0f);
-            if (a.outputAovs) { a.aovOut[2 * (size_t)dst] = aov0; a.aovOut[2 * (size_t)dst + 1] = aov1; }
-            if (a.keysOut) a.keysOut[dst] = sortingKey & 0x1FFFFFu;
+        uint32_t dst = s_base + warpOffset + (incl - mine);
+#pragma unroll
+        for (int i = 0; i < IDK_COMPACT_ITEMS; i++) {
+            if (v[i] != ~0u) {
+                a.aliveOut[dst] = v[i];
+                if (a.keysOut) a.keysOut[dst] = a.keysTmp[first + i];
+                dst++;
+            }
         }
     }
 }

@@ -134,13 +134,14 @@ __global__ void __launch_bounds__(IDK_SORT_THREADS) k_sort_scatter(const uint32_
     }
 }
 
-// Returns the number of kernels launched, or -1 on a launch error. perm[gid] = unsorted slot of the gid-th sorted ray.
-static inline int idk_sort_by_key(IdkSortScratch& s, const uint32_t* keys, uint32_t* perm, const uint32_t* countPtr,
+// Returns the number of kernels launched, or -1 on a launch error. perm[gid] = value (pixel) of the gid-th sorted ray.
+// valsIn = the values that travel with the keys (the alive list); null = slot indices.
+static inline int idk_sort_by_key(IdkSortScratch& s, const uint32_t* keys, const uint32_t* valsIn, uint32_t* perm, const uint32_t* countPtr,
                                   uint32_t capacity, int smCount, cudaStream_t stream) {
     (void)capacity;
     const int grid = smCount * 4;
     const uint32_t* kin[3] = {keys, s.keysB, s.keysA};
-    const uint32_t* vin[3] = {nullptr, s.valsB, s.valsA};
+    const uint32_t* vin[3] = {valsIn, s.valsB, s.valsA};
     uint32_t* kout[3] = {s.keysB, s.keysA, s.keysB};
     uint32_t* vout[3] = {s.valsB, s.valsA, perm};
     for (int p = 0; p < 3; p++) {

@@ -46,10 +46,10 @@ struct IdkPtCtx {
     int skyFaceSize = 0;
 
     // wavefront buffers
-    DevBuf state[2], aov[2], hits, hitXform, debugCost, radiance, aovAlbedoFinal, aovNormalFinal, exportRays;
+    DevBuf state, aov, alive[2], survivors, keysTmp, sortedAlive, hits, hitXform, debugCost, radiance, aovAlbedoFinal, aovNormalFinal;
     DevBuf images[3];
     DevBuf countsDev;              // uint32 counts[IDKPT_MAX_RAY_DEPTH + 1]
-    DevBuf tickets;                // uint32 tickets[2 * (IDKPT_MAX_RAY_DEPTH + 1)] (traverse, shade)
+    DevBuf tickets;                // uint32 tickets[2 * (IDKPT_MAX_RAY_DEPTH + 1)] (traverse, compact)
     DevBuf tileStatus;             // u64 per tile
     DevBuf counters;               // TraceCounters
     DevBuf keys, perm;             // ray sorting
@@ -59,7 +59,7 @@ struct IdkPtCtx {
     bool exportEnabled = false;
 
     // launch configuration
-    int traverseBlocks = 0, traverseBlocksStats = 0, shadeBlocks = 0, traceRaysBlocks = 0;
+    int traverseBlocks = 0, traverseBlocksStats = 0, shadeBlocks = 0, traceRaysBlocks = 0, compactBlocks = 0;
     int traverseVariant = 2;       // 2 = k_traverse2 (phase-scheduled warps), 1 = k_traverse (one ray per lane, reference loop)
     TraverseTuning tune = {12, 4};   // swept on B200 (profiles/r01b_tuning.txt)
     size_t stackBytes = 0;
@@ -144,15 +144,17 @@ static int configure_launches(IdkPtCtx* ctx) {
     ctx->traceRaysBlocks = std::max(1, n) * ctx->smCount;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade, IDK_BLOCK, 0));
     ctx->shadeBlocks = std::max(1, n) * ctx->smCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_compact, IDK_BLOCK, 0));
+    ctx->compactBlocks = std::max(1, std::min(n, 4)) * ctx->smCount;
     return IDKPT_OK;
 }
 
 static int allocate_wavefront(IdkPtCtx* ctx) {
     const size_t n = std::max<uint32_t>(ctx->nLocal, 1);
-    for (int i = 0; i < 2; i++) {
-        CK(ensure(ctx->state[i], n * sizeof(PathState)));
-        CK(ensure(ctx->aov[i], n * 32));
-    }
+    CK(ensure(ctx->state, n * sizeof(PathState)));
+    CK(ensure(ctx->aov, n * 32));
+    for (int i = 0; i < 2; i++) CK(ensure(ctx->alive[i], n * 4));
+    CK(ensure(ctx->survivors, n * 4));
     CK(ensure(ctx->hits, n * 16));
     CK(ensure(ctx->hitXform, n * 4));
     CK(ensure(ctx->debugCost, n * 4));
@@ -165,7 +167,7 @@ static int allocate_wavefront(IdkPtCtx* ctx) {
     }
     CK(ensure(ctx->countsDev, (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
     CK(ensure(ctx->tickets, 2 * (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
-    CK(ensure(ctx->tileStatus, ((n + IDK_BLOCK - 1) / IDK_BLOCK + 1) * sizeof(unsigned long long)));
+    CK(ensure(ctx->tileStatus, ((n + IDK_BLOCK * IDK_COMPACT_ITEMS - 1) / (IDK_BLOCK * IDK_COMPACT_ITEMS) + 1) * sizeof(unsigned long long)));
     CK(cudaMemsetAsync(ctx->tileStatus.p, 0, ctx->tileStatus.bytes, ctx->stream));
     CK(ensure(ctx->counters, sizeof(TraceCounters)));
     ctx->epoch = 0;
@@ -234,9 +236,9 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     DevBuf* all[] = {&ctx->nodes, &ctx->triRec, &ctx->blasTris, &ctx->positions, &ctx->descs, &ctx->instances, &ctx->xforms,
-                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->vtxFrame, &ctx->surfRec, &ctx->state[0], &ctx->state[1], &ctx->aov[0],
-                     &ctx->aov[1], &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
-                     &ctx->aovNormalFinal, &ctx->exportRays, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
+                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->vtxFrame, &ctx->surfRec, &ctx->state, &ctx->aov, &ctx->alive[0],
+                     &ctx->alive[1], &ctx->survivors, &ctx->keysTmp, &ctx->sortedAlive, &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
+                     &ctx->aovNormalFinal, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
                      &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->perm, &ctx->countLog, &ctx->skyFaces};
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ctx->sortScratch);
@@ -426,9 +428,9 @@ IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height) {
     compute_tile_rows(ctx);
     int rc = allocate_wavefront(ctx);
     if (rc) return rc;
-    release(ctx->exportRays);
     release(ctx->keys);
-    release(ctx->perm);
+    release(ctx->keysTmp);
+    release(ctx->sortedAlive);
     ctx->accumulatedSamples = 0;
     return IDKPT_OK;
 }
@@ -490,11 +492,11 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
     const bool aovs = st->OutputAOVs != 0;
     if (sorting) {
         CK(ensure(ctx->keys, (size_t)n * 4));
-        CK(ensure(ctx->perm, (size_t)n * 4));
+        CK(ensure(ctx->keysTmp, (size_t)n * 4));
+        CK(ensure(ctx->sortedAlive, (size_t)n * 4));
         int rc = idk_sort_prepare(ctx->sortScratch, n);
         if (rc) return fail(ctx, IDKPT_ERR_OUT_OF_MEMORY, "idkpt_compute: sort scratch allocation failed");
     }
-    if (ctx->exportEnabled) CK(ensure(ctx->exportRays, (size_t)n * sizeof(GpuWavefrontRay)));
 
     FrameParams f;
     memcpy(f.invProj, frame->InvProjection, sizeof(f.invProj));
@@ -528,29 +530,29 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
         launches++;
 
         size_t e0 = ev.begin();
-        k_raygen<<<rgGrid, rgBlock, 0, ctx->stream>>>(f, (PathState*)ctx->state[0].p);
+        k_raygen<<<rgGrid, rgBlock, 0, ctx->stream>>>(f, (PathState*)ctx->state.p);
         ev.end(e0, 3);
         launches++;
 
-        int cur = 0;
         for (int j = 0; j < st->RayDepth; j++) {
             const bool first = j == 0;
             const bool last = j == st->RayDepth - 1;
-            const uint32_t* perm = nullptr;
+            // alive list of this bounce: slot -> tile pixel (identity for the first hit)
+            const uint32_t* alive = first ? nullptr : (const uint32_t*)ctx->alive[j & 1].p;
             if (sorting && j > 1) {
                 // PathTracer.RaySorting(), PathTracer.cs:273-297: stable sort of the alive list by cached key
                 e0 = ev.begin();
-                int nl = idk_sort_by_key(ctx->sortScratch, (const uint32_t*)ctx->keys.p, (uint32_t*)ctx->perm.p, counts + j, n, ctx->smCount, ctx->stream);
+                int nl = idk_sort_by_key(ctx->sortScratch, (const uint32_t*)ctx->keys.p, alive, (uint32_t*)ctx->sortedAlive.p, counts + j, n, ctx->smCount, ctx->stream);
                 ev.end(e0, 2);
                 if (nl < 0) return fail(ctx, IDKPT_ERR_CUDA, "idkpt_compute: sort launch failed");
                 launches += (uint32_t)nl;
-                perm = (const uint32_t*)ctx->perm.p;
+                alive = (const uint32_t*)ctx->sortedAlive.p;
             }
 
             TraverseArgs ta;
             ta.sc = ctx->sc;
-            ta.state = (const PathState*)ctx->state[cur].p;
-            ta.perm = perm;
+            ta.state = (const PathState*)ctx->state.p;
+            ta.perm = alive;
             ta.count = counts + j;
             ta.ticket = tickets + 2 * j;
             ta.hits = (HitRec*)ctx->hits.p;
@@ -573,32 +575,40 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             ShadeArgs sa;
             sa.sc = ctx->sc;
             sa.f = f;
-            sa.stateIn = (const PathState*)ctx->state[cur].p;
-            sa.stateOut = (PathState*)ctx->state[cur ^ 1].p;
-            sa.aovIn = (const float4*)ctx->aov[cur].p;
-            sa.aovOut = (float4*)ctx->aov[cur ^ 1].p;
-            sa.perm = perm;
+            sa.state = (PathState*)ctx->state.p;
+            sa.aov = (float4*)ctx->aov.p;
+            sa.alive = alive;
             sa.hits = (const HitRec*)ctx->hits.p;
             sa.hitXform = (const uint32_t*)ctx->hitXform.p;
             sa.debugCost = (const float*)ctx->debugCost.p;
             sa.count = counts + j;
-            sa.countOut = counts + j + 1;
-            sa.ticket = tickets + 2 * j + 1;
-            sa.tileStatus = (unsigned long long*)ctx->tileStatus.p;
-            sa.epoch = ++ctx->epoch;
-            sa.keysOut = sorting ? (uint32_t*)ctx->keys.p : nullptr;
+            sa.survivors = (uint32_t*)ctx->survivors.p;
+            sa.keysTmp = sorting ? (uint32_t*)ctx->keysTmp.p : nullptr;
             sa.radiance = (float4*)ctx->radiance.p;
             sa.aovAlbedoFinal = (float4*)ctx->aovAlbedoFinal.p;
             sa.aovNormalFinal = (float4*)ctx->aovNormalFinal.p;
-            sa.exportRays = ctx->exportEnabled ? (GpuWavefrontRay*)ctx->exportRays.p : nullptr;
+            sa.exportState = ctx->exportEnabled ? 1 : 0;
             sa.firstHit = first ? 1 : 0;
             sa.lastBounce = last ? 1 : 0;
             sa.outputAovs = aovs ? 1 : 0;
             e0 = ev.begin();
             k_shade<<<ctx->shadeBlocks, IDK_BLOCK, 0, ctx->stream>>>(sa);
-            ev.end(e0, 1);
             launches++;
-            cur ^= 1;
+            if (!last) {
+                CompactArgs ca;
+                ca.survivors = (const uint32_t*)ctx->survivors.p;
+                ca.keysTmp = sorting ? (const uint32_t*)ctx->keysTmp.p : nullptr;
+                ca.count = counts + j;
+                ca.aliveOut = (uint32_t*)ctx->alive[(j + 1) & 1].p;
+                ca.keysOut = sorting ? (uint32_t*)ctx->keys.p : nullptr;
+                ca.countOut = counts + j + 1;
+                ca.ticket = tickets + 2 * j + 1;
+                ca.tileStatus = (unsigned long long*)ctx->tileStatus.p;
+                ca.epoch = ++ctx->epoch;
+                k_compact<<<ctx->compactBlocks, IDK_BLOCK, 0, ctx->stream>>>(ca);
+                launches++;
+            }
+            ev.end(e0, 1);
         }
 
         e0 = ev.begin();
@@ -739,13 +749,21 @@ IDKPT_API int idkpt_read_wavefront_rays(IdkPtCtx* ctx, GpuWavefrontRay* dst, uin
         ctx->exportEnabled = count != 0;
         return IDKPT_OK;
     }
-    if (!ctx->exportEnabled || !ctx->exportRays.p) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_wavefront_rays: arm the export first (dst = NULL, count = 1) and call idkpt_compute");
+    if (!ctx->exportEnabled) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_wavefront_rays: arm the export first (dst = NULL, count = 1) and call idkpt_compute");
     if (count < (uint64_t)ctx->width * ctx->height) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_wavefront_rays: buffer smaller than width*height");
     CK(cudaSetDevice(ctx->device));
-    const size_t rowBytes = (size_t)ctx->width * sizeof(GpuWavefrontRay);
-    for (size_t i = 0; i < ctx->rows.size(); i++)
-        CK(cudaMemcpyAsync((char*)dst + (size_t)ctx->rows[i] * rowBytes, (char*)ctx->exportRays.p + i * rowBytes, rowBytes, cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<PathState> tmp(ctx->nLocal);
+    CK(cudaMemcpyAsync(tmp.data(), ctx->state.p, (size_t)ctx->nLocal * sizeof(PathState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    for (size_t i = 0; i < ctx->rows.size(); i++) {
+        for (int x = 0; x < ctx->width; x++) {
+            const PathState& s = tmp[i * (size_t)ctx->width + x];
+            GpuWavefrontRay& w = dst[(size_t)ctx->rows[i] * ctx->width + x];
+            w.Origin[0] = s.ox; w.Origin[1] = s.oy; w.Origin[2] = s.oz; w.PreviousIOROrTraverseCost = s.prevIor;
+            w.Throughput[0] = s.tx; w.Throughput[1] = s.ty; w.Throughput[2] = s.tz; w.PackedDirectionX = s.pdx;
+            w.Radiance[0] = s.rx; w.Radiance[1] = s.ry; w.Radiance[2] = s.rz; w.PackedDirectionY = s.pdy;
+        }
+    }
     return IDKPT_OK;
 }
 
