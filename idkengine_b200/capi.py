@@ -53,11 +53,17 @@ class IdkPtStats(ctypes.Structure):
     _fields_ = [("Rays", c_u64), ("BounceRays", c_u64 * IDKPT_MAX_RAY_DEPTH),
                 ("NodePairFetches", c_u64), ("TriangleTests", c_u64), ("InstanceVisits", c_u64), ("Hits", c_u64),
                 ("TotalMs", c_f), ("TraverseMs", c_f), ("ShadeMs", c_f), ("SortMs", c_f), ("OtherMs", c_f),
-                ("KernelLaunches", c_u32), ("TraverseLaunches", c_u32)]
+                ("KernelLaunches", c_u32), ("TraverseLaunches", c_u32),
+                ("BounceTraverseMs", c_f * IDKPT_MAX_RAY_DEPTH), ("BounceShadeMs", c_f * IDKPT_MAX_RAY_DEPTH),
+                ("BounceMaxSteps", c_u32 * IDKPT_MAX_RAY_DEPTH)]
 
     def as_dict(self):
-        d = {n: getattr(self, n) for n, _ in self._fields_ if n != "BounceRays"}
+        arrays = ("BounceRays", "BounceTraverseMs", "BounceShadeMs", "BounceMaxSteps")
+        d = {n: getattr(self, n) for n, _ in self._fields_ if n not in arrays}
         d["BounceRays"] = [int(v) for v in self.BounceRays]
+        d["BounceTraverseMs"] = [float(v) for v in self.BounceTraverseMs]
+        d["BounceShadeMs"] = [float(v) for v in self.BounceShadeMs]
+        d["BounceMaxSteps"] = [int(v) for v in self.BounceMaxSteps]
         return d
 
 

@@ -54,7 +54,7 @@ static_assert(sizeof(PathState) == 64, "PathState must be 64 bytes");
 
 struct HitRec { float bx, by, t; uint32_t tri; };   // 16 bytes, + uint32 transform id in a second array
 
-struct TraceCounters { unsigned long long steps, tris, instances, hits; };
+struct TraceCounters { unsigned long long steps, tris, instances, hits; unsigned int maxSteps[64]; };
 
 // ------------------------------------------------------------------------------------------------
 // Per sample: zero the alive counts and the work tickets, counts[0] = number of primary rays.
@@ -270,6 +270,7 @@ struct TraverseArgs {
     float* debugCost;              // by gid, STATS only
     TraceCounters* counters;       // STATS only
     int traceLights;
+    int bounce;
 };
 
 // Persistent warps: every warp repeatedly claims 32 consecutive slots of the alive list.
@@ -295,7 +296,9 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse(TraverseArgs a) {
             HitRec hit;
             uint32_t xf;
             float cost = 0.0f;
+            const uint32_t stepsBefore = S;
             trace_closest<STATS>(a.sc, o, d, IDK_FLOAT_MAX, a.traceLights != 0, stack, hit, xf, S, T, I, cost);
+            if (STATS) atomicMax(&a.counters->maxSteps[a.bounce & 63], S - stepsBefore);
             reinterpret_cast<float4*>(a.hits)[gid] = make_float4(hit.bx, hit.by, hit.t, __uint_as_float(hit.tri));
             a.hitXform[gid] = xf;
             if (STATS) {
@@ -353,7 +356,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, Travers
     hit.bx = hit.by = 0.0f; hit.t = 0.0f; hit.tri = ~0u;
     const float4* nodes = sc.nodes;
     uint32_t triOffset = 0, top = 2, sp = 0, first = 0, end = 0;
-    uint32_t S = 0, T = 0, I = 0, H = 0;
+    uint32_t S = 0, T = 0, I = 0, H = 0, rayS0 = 0;
     float cost = 0.0f;
 
     for (;;) {
@@ -371,6 +374,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, Travers
                 if (STATS) {
                     a.debugCost[gid] = cost;
                     if (hit.tri != ~0u) H++;
+                    atomicMax(&a.counters->maxSteps[a.bounce & 63], S - rayS0);
                 }
                 haveRay = false;
             }
@@ -405,6 +409,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, Travers
                         }
                         inst = 0;
                         haveRay = true;
+                        rayS0 = S;
                     } else {
                         state = ST_EXIT;
                     }

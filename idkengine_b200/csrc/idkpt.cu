@@ -60,7 +60,9 @@ struct IdkPtCtx {
 
     // launch configuration
     int traverseBlocks = 0, traverseBlocksStats = 0, shadeBlocks = 0, traceRaysBlocks = 0, compactBlocks = 0;
-    int traverseVariant = 2;       // 2 = k_traverse2 (phase-scheduled warps), 1 = k_traverse (one ray per lane, reference loop)
+    int traverse1Blocks = 0, traverse1BlocksStats = 0;
+    int traverseVariant = 3;       // 1 = k_traverse (one ray per lane, reference loop), 2 = k_traverse2 (phase-scheduled warps),
+                                   // 3 = k_traverse for the coherent primary rays, k_traverse2 for every bounce (default)
     TraverseTuning tune = {12, 4};   // swept on B200 (profiles/r01b_tuning.txt)
     size_t stackBytes = 0;
 
@@ -129,6 +131,10 @@ static int configure_launches(IdkPtCtx* ctx) {
     CK(cudaFuncSetAttribute(k_traverse2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_traverse2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     int n = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
+    ctx->traverse1Blocks = std::max(1, n) * ctx->smCount;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, IDK_BLOCK, ctx->stackBytes));
+    ctx->traverse1BlocksStats = std::max(1, n) * ctx->smCount;
     if (ctx->traverseVariant == 1 || ctx->sc.useTlas) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
         ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
@@ -146,6 +152,25 @@ static int configure_launches(IdkPtCtx* ctx) {
     ctx->shadeBlocks = std::max(1, n) * ctx->smCount;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_compact, IDK_BLOCK, 0));
     ctx->compactBlocks = std::max(1, std::min(n, 4)) * ctx->smCount;
+    if (const char* v = getenv("IDKPT_TRAVERSE_BLOCKS_PER_SM")) {   // developer knob
+        const int b = std::max(1, atoi(v));
+        ctx->traverseBlocks = std::min(ctx->traverseBlocks, b * ctx->smCount);
+        ctx->traverseBlocksStats = std::min(ctx->traverseBlocksStats, b * ctx->smCount);
+    }
+    if (const char* v = getenv("IDKPT_CARVEOUT")) {                 // developer knob: same shared-memory carve-out for every kernel
+        const int pct = atoi(v);
+        if (pct >= 0) {
+            cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_traverse2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_traverse2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_shade, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_compact, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_raygen, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_init_sample, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+        }
+    }
     return IDKPT_OK;
 }
 
@@ -216,7 +241,7 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
         return fail(nullptr, IDKPT_ERR_CUDA, "idkpt_create: cudaStreamCreate failed");
     }
     // developer knobs (kernel variant / scheduling thresholds); results are identical for every setting
-    if (const char* v = getenv("IDKPT_TRAVERSE_VARIANT")) ctx->traverseVariant = atoi(v) == 1 ? 1 : 2;
+    if (const char* v = getenv("IDKPT_TRAVERSE_VARIANT")) ctx->traverseVariant = std::max(1, std::min(3, atoi(v)));
     if (const char* v = getenv("IDKPT_TUNE_SETUP")) ctx->tune.setupThreshold = std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("IDKPT_TUNE_LEAF")) ctx->tune.leafThreshold = std::max(1, std::min(32, atoi(v)));
     compute_tile_rows(ctx);
@@ -292,7 +317,11 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     }
 
     int rc;
-    if ((rc = upload(ctx, ctx->nodes, s->BlasNodes, s->BlasNodeCount * sizeof(GpuBlasNode)))) return rc;
+    // nodes and triangle records share one allocation ("bvh"): [nodes | triRec], so that one L2 access-policy window covers both
+    const size_t nodeBytes = ((s->BlasNodeCount * sizeof(GpuBlasNode)) + 255) & ~(size_t)255;
+    const size_t triRecBytes = std::max<size_t>(s->BlasTriangleCount, 1) * 48;
+    CK(ensure(ctx->nodes, nodeBytes + triRecBytes));
+    CK(cudaMemcpyAsync(ctx->nodes.p, s->BlasNodes, s->BlasNodeCount * sizeof(GpuBlasNode), cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = upload(ctx, ctx->blasTris, s->BlasTriangles, s->BlasTriangleCount * sizeof(GpuBlasTriangle)))) return rc;
     if ((rc = upload(ctx, ctx->positions, s->VertexPositions, s->VertexPositionCount * sizeof(PackedVec3)))) return rc;
     if ((rc = upload(ctx, ctx->descs, s->BlasDescs, s->BlasDescCount * sizeof(GpuBlasDesc)))) return rc;
@@ -303,7 +332,6 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     if ((rc = upload(ctx, ctx->vertices, s->Vertices, s->VertexCount * sizeof(GpuVertex)))) return rc;
     if ((rc = upload(ctx, ctx->lights, s->Lights, s->LightCount * sizeof(GpuLight)))) return rc;
     if ((rc = upload(ctx, ctx->tlas, s->TlasNodes, s->UseTlas ? s->TlasNodeCount * sizeof(GpuTlasNode) : 0))) return rc;
-    CK(ensure(ctx->triRec, std::max<size_t>(s->BlasTriangleCount, 1) * 48));
 
     // triangle vertex ids must index the position / vertex arrays
     // (checked on the host copy: cheap relative to the BVH build that produced it)
@@ -326,13 +354,13 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     CK(cudaGetLastError());
     if (s->BlasTriangleCount) {
         const uint32_t n = (uint32_t)s->BlasTriangleCount;
-        k_prepare_triangles<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const int4*)ctx->blasTris.p, (const float*)ctx->positions.p, (float4*)ctx->triRec.p, n);
+        k_prepare_triangles<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const int4*)ctx->blasTris.p, (const float*)ctx->positions.p, (float4*)((char*)ctx->nodes.p + nodeBytes), n);
         CK(cudaGetLastError());
     }
 
     DeviceScene& sc = ctx->sc;
     sc.nodes = (const float4*)ctx->nodes.p;
-    sc.triRec = (const float4*)ctx->triRec.p;
+    sc.triRec = (const float4*)((char*)ctx->nodes.p + nodeBytes);
     sc.blasTris = (const int4*)ctx->blasTris.p;
     sc.descs = (const GpuBlasDesc*)ctx->descs.p;
     sc.instances = (const GpuBlasInstance*)ctx->instances.p;
@@ -353,6 +381,30 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     sc.surfRec = (const float4*)ctx->surfRec.p;
     ctx->counts = *s;
     if ((rc = configure_launches(ctx))) return rc;
+    // Keep the BVH resident in the 126 MB L2: persisting access-policy window over [nodes | triRec] on the render stream.
+    // The wavefront buffers (hundreds of MB per frame) stream through the rest of the cache without evicting the tree.
+    {
+        cudaDeviceProp prop;
+        CK(cudaGetDeviceProperties(&prop, ctx->device));
+        const char* env = getenv("IDKPT_L2_PERSIST");
+        const bool want = !(env && atoi(env) == 0);
+        cudaStreamAttrValue attr;
+        memset(&attr, 0, sizeof(attr));
+        if (want && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
+            const size_t bvhBytes = nodeBytes + triRecBytes;
+            const size_t setAside = std::min<size_t>((size_t)prop.persistingL2CacheMaxSize, std::max<size_t>(bvhBytes, 1 << 20));
+            CK(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, setAside));
+            const size_t window = std::min<size_t>(bvhBytes, (size_t)prop.accessPolicyMaxWindowSize);
+            attr.accessPolicyWindow.base_ptr = ctx->nodes.p;
+            attr.accessPolicyWindow.num_bytes = window;
+            attr.accessPolicyWindow.hitRatio = window <= setAside ? 1.0f : (float)((double)setAside / (double)window);
+            attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+            attr.accessPolicyWindow.missProp = cudaAccessPropertyNormal;
+        } else {
+            attr.accessPolicyWindow.num_bytes = 0;
+        }
+        CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveScene = true;
     ctx->accumulatedSamples = 0;
@@ -452,7 +504,7 @@ IDKPT_API int idkpt_set_accumulated_samples(IdkPtCtx* ctx, uint32_t n) {
 struct EventPool {
     IdkPtCtx* ctx;
     size_t used = 0;
-    struct Span { size_t a, b; int cat; };
+    struct Span { size_t a, b; int cat; int bounce; };
     std::vector<Span> spans;
     bool enabled;
     cudaEvent_t get() {
@@ -469,11 +521,11 @@ struct EventPool {
         cudaEventRecord(get(), ctx->stream);
         return i;
     }
-    void end(size_t a, int cat) {
+    void end(size_t a, int cat, int bounce = -1) {
         if (!enabled) return;
         size_t i = used;
         cudaEventRecord(get(), ctx->stream);
-        spans.push_back({a, i, cat});
+        spans.push_back({a, i, cat, bounce});
     }
 };
 
@@ -560,15 +612,16 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             ta.debugCost = (float*)ctx->debugCost.p;
             ta.counters = (TraceCounters*)ctx->counters.p;
             ta.traceLights = st->Gpu.DoTraceLights;
+            ta.bounce = j;
             e0 = ev.begin();
-            if (ctx->traverseVariant == 1 || ctx->sc.useTlas) {
-                if (wantStats) k_traverse<true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
-                else k_traverse<false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
+            if (ctx->traverseVariant == 1 || ctx->sc.useTlas || (ctx->traverseVariant == 3 && first)) {
+                if (wantStats) k_traverse<true><<<ctx->traverse1BlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
+                else k_traverse<false><<<ctx->traverse1Blocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
             } else {
                 if (wantStats) k_traverse2<true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta, ctx->tune);
                 else k_traverse2<false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta, ctx->tune);
             }
-            ev.end(e0, 0);
+            ev.end(e0, 0, j);
             launches++;
             traverseLaunches++;
 
@@ -608,7 +661,7 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                 k_compact<<<ctx->compactBlocks, IDK_BLOCK, 0, ctx->stream>>>(ca);
                 launches++;
             }
-            ev.end(e0, 1);
+            ev.end(e0, 1, j);
         }
 
         e0 = ev.begin();
@@ -645,13 +698,14 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             stats->TriangleTests = tc.tris;
             stats->InstanceVisits = tc.instances;
             stats->Hits = tc.hits;
+            for (int j = 0; j < IDKPT_MAX_RAY_DEPTH; j++) stats->BounceMaxSteps[j] = tc.maxSteps[j];
         }
         for (const EventPool::Span& sp : ev.spans) {
             float ms = 0.0f;
             cudaEventElapsedTime(&ms, ctx->events[sp.a], ctx->events[sp.b]);
             switch (sp.cat) {
-                case 0: stats->TraverseMs += ms; break;
-                case 1: stats->ShadeMs += ms; break;
+                case 0: stats->TraverseMs += ms; if (sp.bounce >= 0) stats->BounceTraverseMs[sp.bounce] += ms; break;
+                case 1: stats->ShadeMs += ms; if (sp.bounce >= 0) stats->BounceShadeMs[sp.bounce] += ms; break;
                 case 2: stats->SortMs += ms; break;
                 case 3: stats->OtherMs += ms; break;
                 default: stats->TotalMs = ms; break;

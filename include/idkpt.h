@@ -121,6 +121,9 @@ typedef struct IdkPtStats {
     float    OtherMs;                            /* ray-gen + accumulate */
     uint32_t KernelLaunches;
     uint32_t TraverseLaunches;
+    float    BounceTraverseMs[IDKPT_MAX_RAY_DEPTH];   /* per bounce, summed over samples */
+    float    BounceShadeMs[IDKPT_MAX_RAY_DEPTH];      /* shade + compaction */
+    uint32_t BounceMaxSteps[IDKPT_MAX_RAY_DEPTH];     /* longest ray (node-pair fetches) per bounce (valid if CollectStats) */
 } IdkPtStats;
 
 typedef enum IdkPtImage {
