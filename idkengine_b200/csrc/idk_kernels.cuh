@@ -33,6 +33,7 @@ struct DeviceScene {
     int skyFaceSize;
     const float4* tlasNodes;      // 2 x float4 per GpuTlasNode, root at 0 (USE_TLAS path, BVHIntersect.glsl:205-272)
     int useTlas;
+    int treeletNodes;             // node indices < treeletNodes (BFS-first re-layout, single-BLAS scenes) are staged in shared memory
     const float4* vtxFrame;       // device-private, 2 x float4 per vertex: decoded (normal.xyz, tangent.x) (tangent.yz, 0, 0)
     const float4* surfRec;        // device-private, 5 x float4 per mesh: GetSurface + SurfaceApplyModificatons, see k_prepare_surfaces
 };
@@ -337,14 +338,46 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse(TraverseArgs a) {
 // else can run. Traversal stacks live in shared memory, one column per thread (the reference's layout).
 struct TraverseTuning { int setupThreshold; int leafThreshold; };
 
-template <bool STATS>
+// TMA (bulk async copy) staging of the hot top of the BVH into shared memory: one elected thread arms an mbarrier with
+// the byte count and issues cp.async.bulk global -> shared; every thread then waits on the barrier phase.
+__device__ __forceinline__ void tma_stage_treelet(void* smemDst, const void* gmemSrc, uint32_t bytes, uint64_t* mbar) {
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(mbar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smemDst);
+        const uint32_t chunk = 16384u;
+        for (uint32_t off = 0; off < bytes; off += chunk) {
+            const uint32_t n = min(chunk, bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + off), "l"((const char*)gmemSrc + off), "r"(n), "r"(bar) : "memory");
+        }
+    }
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(bar), "r"(0u) : "memory");
+    }
+}
+
+template <bool STATS, bool TREELET>
 __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, TraverseTuning tune) {
-    extern __shared__ uint32_t s_stack[];
+    // dynamic shared memory: [treelet: treeletNodes x 32 B][traversal stacks: stackSize x IDK_BLOCK x 4 B]
+    extern __shared__ __align__(128) unsigned char s_dyn[];
+    __shared__ __align__(8) uint64_t s_mbar;
+    const DeviceScene& sc = a.sc;
+    const uint32_t treeletNodes = TREELET ? (uint32_t)sc.treeletNodes : 0u;
+    const float4* s_treelet = reinterpret_cast<const float4*>(s_dyn);
+    uint32_t* s_stack = reinterpret_cast<uint32_t*>(s_dyn + (size_t)treeletNodes * 32);
+    if (TREELET && treeletNodes) tma_stage_treelet(s_dyn, sc.nodes, treeletNodes * 32u, &s_mbar);
     uint32_t* stack = s_stack + threadIdx.x;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t laneLt = (1u << lane) - 1u;
     const uint32_t count = *a.count;
-    const DeviceScene& sc = a.sc;
     enum { ST_SETUP = 0, ST_BOX = 1, ST_LEAF = 2, ST_EXIT = 3 };
 
     int state = ST_SETUP;
@@ -461,8 +494,14 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, Travers
             // ------------------------------------------------------------------ BOX (one sibling pair)
             if (state == ST_BOX) {
                 if (STATS) { S++; cost += 1.0f; }
-                const float4* np = nodes + 2 * (size_t)top;
-                const float4 lA = ldg4(np), lB = ldg4(np + 1), rA = ldg4(np + 2), rB = ldg4(np + 3);
+                float4 lA, lB, rA, rB;
+                if (TREELET && top < treeletNodes) {       // hot top of the tree: shared memory (single-BLAS scenes, nodes == sc.nodes)
+                    const float4* np = s_treelet + 2 * (size_t)top;
+                    lA = np[0]; lB = np[1]; rA = np[2]; rB = np[3];
+                } else {
+                    const float4* np = nodes + 2 * (size_t)top;
+                    lA = ldg4(np); lB = ldg4(np + 1); rA = ldg4(np + 2); rB = ldg4(np + 3);
+                }
                 const int lChild = __float_as_int(lA.w), lCount = __float_as_int(lB.w);
                 const int rChild = __float_as_int(rA.w), rCount = __float_as_int(rB.w);
                 float tMinLeft, tMinRight;

@@ -65,6 +65,8 @@ struct IdkPtCtx {
                                    // 3 = k_traverse for the coherent primary rays, k_traverse2 for every bounce (default)
     TraverseTuning tune = {12, 4};   // swept on B200 (profiles/r01b_tuning.txt)
     size_t stackBytes = 0;
+    size_t traverse2Smem = 0;      // treelet + stacks
+    int treeletNodes = 0;
 
     std::vector<cudaEvent_t> events;
 
@@ -128,8 +130,11 @@ static int configure_launches(IdkPtCtx* ctx) {
     CK(cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
-    CK(cudaFuncSetAttribute(k_traverse2<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
-    CK(cudaFuncSetAttribute(k_traverse2<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
+    ctx->traverse2Smem = ctx->stackBytes + (size_t)ctx->treeletNodes * 32;
+    CK(cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    CK(cudaFuncSetAttribute(k_traverse2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    CK(cudaFuncSetAttribute(k_traverse2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    CK(cudaFuncSetAttribute(k_traverse2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
     int n = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
     ctx->traverse1Blocks = std::max(1, n) * ctx->smCount;
@@ -141,9 +146,11 @@ static int configure_launches(IdkPtCtx* ctx) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, IDK_BLOCK, ctx->stackBytes));
         ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
     } else {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false>, IDK_BLOCK, ctx->stackBytes));
+        if (ctx->treeletNodes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false, true>, IDK_BLOCK, ctx->traverse2Smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false, false>, IDK_BLOCK, ctx->traverse2Smem));
         ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true>, IDK_BLOCK, ctx->stackBytes));
+        if (ctx->treeletNodes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true, true>, IDK_BLOCK, ctx->traverse2Smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true, false>, IDK_BLOCK, ctx->traverse2Smem));
         ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_rays, IDK_BLOCK, ctx->stackBytes));
@@ -162,8 +169,8 @@ static int configure_launches(IdkPtCtx* ctx) {
         if (pct >= 0) {
             cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(k_traverse2<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(k_traverse2<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_traverse2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_shade, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_compact, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_raygen, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -197,6 +204,52 @@ static int allocate_wavefront(IdkPtCtx* ctx) {
     CK(ensure(ctx->counters, sizeof(TraceCounters)));
     ctx->epoch = 0;
     return IDKPT_OK;
+}
+
+// Device-private node layout for single-BLAS scenes: the first `pairs` sibling pairs in breadth-first order are moved to
+// the front of the array (node indices 2 .. 2*pairs+1) so that the hot top of the tree is one contiguous block that a
+// single bulk copy (TMA) can stage into shared memory; all remaining pairs keep their relative order. Child pointers are
+// rewritten; leaves (triangle ranges) are untouched, so traversal order and results are unchanged.
+static int relayout_treelet(const GpuBlasNode* src, uint32_t nodeCount, uint32_t wantPairs, std::vector<GpuBlasNode>& out) {
+    const uint32_t pairCount = nodeCount / 2;            // pair p = nodes 2p, 2p+1 (pair 0 = pad + root)
+    if (pairCount < 2) return 0;
+    std::vector<uint32_t> newOf(pairCount, 0xFFFFFFFFu), order;
+    order.reserve(pairCount);
+    std::vector<uint32_t> queue;
+    queue.push_back(1);                                  // children of the root
+    size_t head = 0;
+    const uint32_t treeletPairs = std::min(wantPairs, pairCount - 1);
+    while (head < queue.size() && order.size() < treeletPairs) {
+        const uint32_t p = queue[head++];
+        newOf[p] = (uint32_t)order.size() + 1;
+        order.push_back(p);
+        for (int c = 0; c < 2; c++) {
+            const GpuBlasNode& n = src[2 * p + c];
+            if (n.TriCount == 0) {
+                if (n.TriStartOrChild < 2 || (uint32_t)n.TriStartOrChild + 1 >= nodeCount || (n.TriStartOrChild & 1)) return -1;
+                queue.push_back((uint32_t)n.TriStartOrChild / 2);
+            }
+        }
+    }
+    const uint32_t inTreelet = (uint32_t)order.size();
+    for (uint32_t p = 1; p < pairCount; p++)
+        if (newOf[p] == 0xFFFFFFFFu) { newOf[p] = (uint32_t)order.size() + 1; order.push_back(p); }
+    out.assign(nodeCount, GpuBlasNode{});
+    out[0] = src[0];
+    out[1] = src[1];
+    if (src[1].TriCount == 0) out[1].TriStartOrChild = 2;
+    for (uint32_t i = 0; i < order.size(); i++) {
+        const uint32_t p = order[i], np = i + 1;
+        for (int c = 0; c < 2; c++) {
+            GpuBlasNode n = src[2 * p + c];
+            if (n.TriCount == 0) {
+                if (n.TriStartOrChild < 2 || (uint32_t)n.TriStartOrChild + 1 >= nodeCount || (n.TriStartOrChild & 1)) return -1;
+                n.TriStartOrChild = (int32_t)(2 * newOf[(uint32_t)n.TriStartOrChild / 2]);
+            }
+            out[2 * np + c] = n;
+        }
+    }
+    return (int)inTreelet;
 }
 
 extern "C" {
@@ -321,7 +374,20 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     const size_t nodeBytes = ((s->BlasNodeCount * sizeof(GpuBlasNode)) + 255) & ~(size_t)255;
     const size_t triRecBytes = std::max<size_t>(s->BlasTriangleCount, 1) * 48;
     CK(ensure(ctx->nodes, nodeBytes + triRecBytes));
-    CK(cudaMemcpyAsync(ctx->nodes.p, s->BlasNodes, s->BlasNodeCount * sizeof(GpuBlasNode), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->treeletNodes = 0;
+    std::vector<GpuBlasNode> relaid;
+    {
+        const char* env = getenv("IDKPT_TREELET_PAIRS");
+        const uint32_t wantPairs = env ? (uint32_t)std::min(768, std::max(0, atoi(env))) : 0u;   // default off: measured no gain over the L1 (profiles/r01d_treelet.txt)
+        if (wantPairs > 0 && !s->UseTlas && s->BlasInstanceCount == 1 && s->BlasDescCount == 1 && s->BlasDescs[0].NodeOffset == 0 &&
+            s->BlasNodeCount < (1ull << 31) && (s->BlasNodeCount & 1) == 0) {
+            const int got = relayout_treelet(s->BlasNodes, (uint32_t)s->BlasNodeCount, wantPairs, relaid);
+            if (got > 0) ctx->treeletNodes = 2 * got + 2;
+            else relaid.clear();
+        }
+    }
+    CK(cudaMemcpyAsync(ctx->nodes.p, relaid.empty() ? s->BlasNodes : relaid.data(), s->BlasNodeCount * sizeof(GpuBlasNode), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));   // `relaid` is a local
     if ((rc = upload(ctx, ctx->blasTris, s->BlasTriangles, s->BlasTriangleCount * sizeof(GpuBlasTriangle)))) return rc;
     if ((rc = upload(ctx, ctx->positions, s->VertexPositions, s->VertexPositionCount * sizeof(PackedVec3)))) return rc;
     if ((rc = upload(ctx, ctx->descs, s->BlasDescs, s->BlasDescCount * sizeof(GpuBlasDesc)))) return rc;
@@ -377,6 +443,7 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     sc.stackSize = std::max(1, s->BlasStackSize);
     sc.tlasNodes = (const float4*)ctx->tlas.p;
     sc.useTlas = s->UseTlas ? 1 : 0;
+    sc.treeletNodes = ctx->treeletNodes;
     sc.vtxFrame = (const float4*)ctx->vtxFrame.p;
     sc.surfRec = (const float4*)ctx->surfRec.p;
     ctx->counts = *s;
@@ -618,8 +685,13 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                 if (wantStats) k_traverse<true><<<ctx->traverse1BlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
                 else k_traverse<false><<<ctx->traverse1Blocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
             } else {
-                if (wantStats) k_traverse2<true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta, ctx->tune);
-                else k_traverse2<false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta, ctx->tune);
+                if (ctx->treeletNodes) {
+                    if (wantStats) k_traverse2<true, true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->traverse2Smem, ctx->stream>>>(ta, ctx->tune);
+                    else k_traverse2<false, true><<<ctx->traverseBlocks, IDK_BLOCK, ctx->traverse2Smem, ctx->stream>>>(ta, ctx->tune);
+                } else {
+                    if (wantStats) k_traverse2<true, false><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->traverse2Smem, ctx->stream>>>(ta, ctx->tune);
+                    else k_traverse2<false, false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->traverse2Smem, ctx->stream>>>(ta, ctx->tune);
+                }
             }
             ev.end(e0, 0, j);
             launches++;

@@ -240,6 +240,34 @@ def test_large_config_properties():
     assert_same(g, o)
 
 
+def test_treelet_and_kernel_variants_agree(atrium_small):
+    """Developer knobs select other code paths (plain loop everywhere, phase-scheduled everywhere, TMA-staged treelet with
+    the BFS-first node re-layout): every one of them must reproduce the oracle bit for bit."""
+    import os
+    scene, cam = atrium_small
+    s = capi.default_settings()
+    s.RayDepth = 5
+    rays = random_rays(6000, -6.0, 6.0, 31)
+    ref = ol.trace_rays(scene, rays)
+    for env in ({"IDKPT_TRAVERSE_VARIANT": "1"}, {"IDKPT_TRAVERSE_VARIANT": "2"},
+                {"IDKPT_TRAVERSE_VARIANT": "2", "IDKPT_TREELET_PAIRS": "192"}, {"IDKPT_TREELET_PAIRS": "5"},
+                {"IDKPT_TRAVERSE_VARIANT": "2", "IDKPT_TREELET_PAIRS": "100000"}):
+        old = {k: os.environ.get(k) for k in env}
+        os.environ.update(env)
+        try:
+            assert_same(*run_both(scene, cam, 160, 96, s))
+            with PathTracer(32, 32) as pt:
+                pt.SetScene(scene)
+                g, _ = pt.TraceRays(rays)
+            assert_hits_equal(g, ref)
+        finally:
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
+
+
 def test_errors(cornell):
     scene, cam = cornell
     with PathTracer(32, 32) as pt:
