@@ -379,6 +379,13 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, Travers
     const uint32_t laneLt = (1u << lane) - 1u;
     const uint32_t count = *a.count;
     enum { ST_SETUP = 0, ST_BOX = 1, ST_LEAF = 2, ST_EXIT = 3 };
+    // Latency regime (few rays, e.g. late bounces or a 1/8 screen tile): spread the rays over ALL resident warps instead
+    // of packing 32 per warp -- a warp that carries few rays has short BOX/LEAF/SETUP rounds and little L1 wavefront
+    // serialisation, so the longest ray (which bounds the launch) finishes sooner. quota = rays per warp, 32 in the bulk.
+    const uint32_t totalWarps = gridDim.x * (IDK_BLOCK / 32);
+    const uint32_t quota = min(32u, max(1u, (count + totalWarps - 1) / totalWarps));
+    const int setupThreshold = max(1, min(tune.setupThreshold, (int)(quota * 3 / 8)));
+    const int leafThreshold = max(1, min(tune.leafThreshold, (int)(quota / 8)));
 
     int state = ST_SETUP;
     bool haveRay = false, finished = false, blasHit = false;
@@ -398,7 +405,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, Travers
         const uint32_t mLeaf = __ballot_sync(0xffffffffu, state == ST_LEAF);
         if ((mSetup | mBox | mLeaf) == 0u) break;
 
-        if (mSetup && (__popc(mSetup) >= tune.setupThreshold || (mBox | mLeaf) == 0u)) {
+        if (mSetup && (__popc(mSetup) >= setupThreshold || (mBox | mLeaf) == 0u)) {
             // ------------------------------------------------------------------ SETUP
             const bool mine = state == ST_SETUP;
             if (mine && haveRay && inst >= sc.instanceCount) {
@@ -411,7 +418,8 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, Travers
                 }
                 haveRay = false;
             }
-            const bool needFetch = mine && !haveRay;
+            const bool needFetch = mine && !haveRay && lane < quota;
+            if (mine && !haveRay && lane >= quota) state = ST_EXIT;
             const uint32_t fm = __ballot_sync(0xffffffffu, needFetch);
             if (fm) {
                 const int leader = __ffs(fm) - 1;
@@ -469,7 +477,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse2(TraverseArgs a, Travers
                     inst++;
                 }
             }
-        } else if (mLeaf && (__popc(mLeaf) >= tune.leafThreshold || mBox == 0u)) {
+        } else if (mLeaf && (__popc(mLeaf) >= leafThreshold || mBox == 0u)) {
             // ------------------------------------------------------------------ LEAF (one triangle)
             if (state == ST_LEAF) {
                 const float4* tr = sc.triRec + 3 * (size_t)first;

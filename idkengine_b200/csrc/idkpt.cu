@@ -52,7 +52,7 @@ struct IdkPtCtx {
     DevBuf tickets;                // uint32 tickets[2 * (IDKPT_MAX_RAY_DEPTH + 1)] (traverse, compact)
     DevBuf tileStatus;             // u64 per tile
     DevBuf counters;               // TraceCounters
-    DevBuf keys, perm;             // ray sorting
+    DevBuf keys;                   // ray sorting: key per slot of the compacted alive list
     DevBuf countLog;               // per-sample copies of the alive counts (stats only)
     IdkSortScratch sortScratch;
     uint32_t epoch = 0;
@@ -317,7 +317,7 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
                      &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->vtxFrame, &ctx->surfRec, &ctx->state, &ctx->aov, &ctx->alive[0],
                      &ctx->alive[1], &ctx->survivors, &ctx->keysTmp, &ctx->sortedAlive, &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
                      &ctx->aovNormalFinal, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
-                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->perm, &ctx->countLog, &ctx->skyFaces};
+                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->countLog, &ctx->skyFaces};
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ctx->sortScratch);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);

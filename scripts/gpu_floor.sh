@@ -1,2 +1,2 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for l2 in 1 0; do for v in 3 2; do echo "== L2_PERSIST $l2 VARIANT $v"; IDKPT_L2_PERSIST=$l2 IDKPT_TRAVERSE_VARIANT=$v python scripts/per_bounce.py; done; done
+for p in 0 4 8 16 32; do echo "== PREFETCH $p"; IDKPT_TUNE_PREFETCH=$p python scripts/per_bounce.py; done
