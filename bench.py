@@ -113,7 +113,8 @@ def workload_config(args, world, scene):
                     f"({args.ray_depth - 1} bounces) 1spp RR on, sort {'on' if args.sort else 'off'}, constant sky, constant textures",
         "triangles": int(info["source_triangles"]), "blas_triangles": int(info["triangles"]), "blas_nodes": int(info["nodes"]),
         "blas_stack_size": int(scene.blas_stack_size),
-        "parallelism": f"screen tiles: {STRIPE}-row stripes round-robin over {world} GPU(s), scene replicated, 1 all-gather/frame",
+        "parallelism": f"screen tiles: {STRIPE}-row stripes round-robin over {world} GPU(s), scene replicated, tile gather fused into "
+                       f"FinalDraw over NVLink peer memory (IDKPT_GATHER=nccl: one NCCL all-gather per frame)",
         "l2": "per-step working set (2x64B path state + hits, ~330 MB at 1080p) exceeds the 126 MB L2; the 22 MB BVH is "
               "re-read every bounce and is L2-resident by design (SURVEY 8d)",
     }
@@ -200,7 +201,16 @@ def run_ours(args, rank, world, local_rank):
     local = torch.as_tensor(multigpu.DeviceArray(ptr, (len(rows), args.width, 4)), device=dev)
     pinned = [torch.empty((args.height, args.width, 4), dtype=torch.float32).pin_memory() for _ in range(2)]
     copy_stream = torch.cuda.Stream(device=dev)
-    gatherer = multigpu.TileGatherer(args.height, args.width, 4, STRIPE, world, dev) if world > 1 else None
+    # N > 1: the tile all-gather is fused into Compute() over NVLink peer memory (CUDA IPC); IDKPT_GATHER=nccl selects the
+    # torch.distributed all_gather + de-interleave fallback instead.
+    peer_gather = world > 1 and os.environ.get("IDKPT_GATHER", "peer") != "nccl"
+    gatherer = multigpu.TileGatherer(args.height, args.width, 4, STRIPE, world, dev) if (world > 1 and not peer_gather) else None
+    if peer_gather:
+        def exchange(blob):
+            out = [None] * world
+            dist.all_gather_object(out, blob)
+            return out
+        pt.EnablePeerGather(rank, world, exchange)
 
     def barrier():
         if world > 1:
@@ -214,6 +224,9 @@ def run_ours(args, rank, world, local_rank):
         if world == 1:
             if e2e:
                 pt.PresentAsync(pinned[k & 1].data_ptr(), pinned[k & 1].numel() * 4)
+        elif peer_gather:
+            if e2e and rank == 0:
+                pt.PresentAsync(pinned[k & 1].data_ptr(), pinned[k & 1].numel() * 4, which=capi.IDKPT_IMAGE_GATHERED)
         else:
             torch.cuda.current_stream().wait_stream(copy_stream)     # the previous read-back still reads gatherer.full
             full = gatherer.gather(local)
@@ -224,7 +237,7 @@ def run_ours(args, rank, world, local_rank):
         return st
 
     def e2e_drain():
-        if world == 1:
+        if world == 1 or peer_gather:
             pt.PresentWait()
         else:
             copy_stream.synchronize()
@@ -256,13 +269,15 @@ def run_ours(args, rank, world, local_rank):
         st = pt.Compute()
         dev_ms += st.TotalMs; trav_ms += st.TraverseMs; shade_ms += st.ShadeMs
         rays += st.Rays; launches += st.KernelLaunches; trav_launches += st.TraverseLaunches
-        if world > 1:
+        if world > 1 and not peer_gather:
             ev0.record()
             gatherer.gather(local)
             ev1.record()
             ev1.synchronize()
             gather_ms += ev0.elapsed_time(ev1)
             launches += 1
+        elif world > 1:
+            gather_ms += st.OtherMs        # ray-gen + fused accumulate/scatter + arrival wait (inside Compute)
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     clocks = sampler.stop() if rank == 0 else None
@@ -286,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
-    job_ms = reduce(dev_ms + gather_ms, MAX)        # device time, max over ranks
+    job_ms = reduce(dev_ms + (0.0 if peer_gather else gather_ms), MAX)        # device time, max over ranks
     total_rays = reduce(rays, SUM)
     total_launches = int(reduce(launches, SUM))
     e2e_ms = reduce(e2e_ms, MAX)

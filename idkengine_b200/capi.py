@@ -67,7 +67,8 @@ class IdkPtStats(ctypes.Structure):
         return d
 
 
-IDKPT_IMAGE_RESULT, IDKPT_IMAGE_ALBEDO, IDKPT_IMAGE_NORMAL = 0, 1, 2
+IDKPT_IMAGE_RESULT, IDKPT_IMAGE_ALBEDO, IDKPT_IMAGE_NORMAL, IDKPT_IMAGE_GATHERED = 0, 1, 2, 3
+IDKPT_GATHER_HANDLE_BYTES = 256
 IDKPT_ARRAY_MESH_TRANSFORMS, IDKPT_ARRAY_MESHES, IDKPT_ARRAY_MATERIALS, IDKPT_ARRAY_LIGHTS = 0, 1, 2, 3
 
 # every symbol include/idkpt.h declares
@@ -75,6 +76,7 @@ EXPORTS = [
     "idkpt_create", "idkpt_destroy", "idkpt_last_error", "idkpt_set_scene", "idkpt_update_range", "idkpt_set_sky",
     "idkpt_resize", "idkpt_reset_accumulation", "idkpt_accumulated_samples", "idkpt_set_accumulated_samples",
     "idkpt_compute", "idkpt_read_result", "idkpt_write_result", "idkpt_present_async", "idkpt_present_wait",
+    "idkpt_gather_export", "idkpt_gather_import", "idkpt_gather_device_ptr",
     "idkpt_result_device_ptr", "idkpt_tile_rows",
     "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_abi_version",
 ]
@@ -183,6 +185,12 @@ def load(path=None):
     L.idkpt_present_async.argtypes = [c_vp, c_i32, c_vp, c_u64]
     L.idkpt_present_wait.restype = c_i32
     L.idkpt_present_wait.argtypes = [c_vp]
+    L.idkpt_gather_export.restype = c_i32
+    L.idkpt_gather_export.argtypes = [c_vp, c_vp, c_u64]
+    L.idkpt_gather_import.restype = c_i32
+    L.idkpt_gather_import.argtypes = [c_vp, c_i32, c_i32, c_vp, c_u64]
+    L.idkpt_gather_device_ptr.restype = c_i32
+    L.idkpt_gather_device_ptr.argtypes = [c_vp, P(c_vp), P(c_u64)]
     L.idkpt_result_device_ptr.restype = c_i32
     L.idkpt_result_device_ptr.argtypes = [c_vp, c_i32, P(c_vp), P(c_u64)]
     L.idkpt_tile_rows.restype = c_i32

@@ -1069,6 +1069,37 @@ __device__ __forceinline__ f3 turbo_colormap(float x) {
                (((v0 * 0.10667330f + v1 * 12.64194608f) + v2 * -60.58204836f) + v3 * 110.36276771f) + (w0 * -89.90310912f + w1 * 27.34824973f));
 }
 
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU: FinalDraw fused with the tile all-gather over NVLink peer memory. Every rank owns a full-size image
+// (double-buffered) that all ranks can write (CUDA IPC mappings). The accumulate kernel of the last sample stores each
+// finished pixel into its own Result tile AND into every rank's full image at the pixel's final (de-interleaved)
+// position; the last CTA to finish then raises this rank's flag on every peer (release), and a one-warp kernel waits
+// until all peers' flags for this frame have arrived (acquire). No NCCL call, no separate de-interleave pass.
+#define IDK_MAX_PEERS 16
+struct GatherArgs {
+    float4* peerImage[IDK_MAX_PEERS];      // this frame's full image on every rank (own rank included)
+    uint32_t* peerFlags[IDK_MAX_PEERS];    // flags[world] on every rank; entry [rank] is written by `rank`
+    const int* tileRows;                   // owned image rows, ascending (device)
+    uint32_t* doneCounter;                 // CTA completion counter (zeroed per frame)
+    int world, rank, width;
+    uint32_t epoch;
+};
+
+__global__ void __launch_bounds__(IDK_BLOCK) k_accumulate_scatter(const float4* __restrict__ radiance, float4* __restrict__ result,
+                                                                  uint32_t count, uint32_t accumulatedSamples, int debugTraversal,
+                                                                  GatherArgs g);
+
+__global__ void __launch_bounds__(32) k_gather_wait(const uint32_t* flags, int world, uint32_t epoch, uint32_t* timedOut) {
+    const int p = threadIdx.x;
+    if (p < world) {
+        const long long t0 = clock64();
+        while (*((volatile const uint32_t*)&flags[p]) != epoch) {
+            if (clock64() - t0 > 6000000000ll) { *timedOut = 1u; break; }   // ~3 s: a peer died; fail instead of hanging the GPU
+        }
+    }
+    __threadfence_system();
+}
+
 __global__ void __launch_bounds__(IDK_BLOCK) k_accumulate(const float4* __restrict__ radiance, const float4* __restrict__ aovAlbedo,
                                                           const float4* __restrict__ aovNormal, float4* __restrict__ result,
                                                           float4* __restrict__ albedo, float4* __restrict__ normal,
@@ -1088,5 +1119,50 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_accumulate(const float4* __restri
             albedo[i] = make_float4(oa.x, oa.y, oa.z, 1.0f);
             normal[i] = make_float4(on.x, on.y, on.z, 1.0f);
         }
+    }
+}
+
+
+__global__ void __launch_bounds__(IDK_BLOCK) k_accumulate_scatter(const float4* __restrict__ radiance, float4* __restrict__ result,
+                                                                  uint32_t count, uint32_t accumulatedSamples, int debugTraversal,
+                                                                  GatherArgs g) {
+    __shared__ bool s_last;
+    const float w = 1.0f / ((float)accumulatedSamples + 1.0f);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const float4 r = radiance[i];
+        f3 nr = mk3(r.x, r.y, r.z);
+        if (debugTraversal) nr = turbo_colormap(r.w / 150.0f);
+        const float4 last = result[i];
+        const f3 o = mix3(mk3(last.x, last.y, last.z), nr, w);
+        const float4 v = make_float4(o.x, o.y, o.z, 1.0f);
+        result[i] = v;
+        const uint32_t row = i / (uint32_t)g.width, x = i - row * (uint32_t)g.width;
+        const size_t dst = (size_t)g.tileRows[row] * (size_t)g.width + x;
+        for (int p = 0; p < g.world; p++) g.peerImage[p][dst] = v;      // 16-byte stores over NVLink (P2P)
+    }
+    // release: all of this CTA's peer stores, then count it; the last CTA publishes the flag on every rank
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(g.doneCounter, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (s_last) {
+        __threadfence_system();
+        if ((int)threadIdx.x < g.world) {
+            *((volatile uint32_t*)&g.peerFlags[threadIdx.x][g.rank]) = g.epoch;
+            __threadfence_system();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(IDK_BLOCK) k_accumulate_aov(const float4* __restrict__ aovAlbedo, const float4* __restrict__ aovNormal,
+                                                              float4* __restrict__ albedo, float4* __restrict__ normal,
+                                                              uint32_t count, uint32_t accumulatedSamples) {
+    const float w = 1.0f / ((float)accumulatedSamples + 1.0f);
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < count; i += gridDim.x * blockDim.x) {
+        const float4 la = albedo[i], ln = normal[i], a = aovAlbedo[i], n = aovNormal[i];
+        const f3 oa = mix3(mk3(la.x, la.y, la.z), mk3(a.x, a.y, a.z), w);
+        const f3 on = mix3(mk3(ln.x, ln.y, ln.z), mk3(n.x, n.y, n.z), w);
+        albedo[i] = make_float4(oa.x, oa.y, oa.z, 1.0f);
+        normal[i] = make_float4(on.x, on.y, on.z, 1.0f);
     }
 }

@@ -70,6 +70,15 @@ struct IdkPtCtx {
 
     std::vector<cudaEvent_t> events;
 
+    // multi-GPU gather over NVLink peer memory (CUDA IPC): full-size images (double-buffered) + arrival flags per rank
+    int gatherWorld = 0, gatherRank = 0;
+    DevBuf gatherImage[2], gatherFlags[2], gatherRows, gatherScratch;     // own buffers (exported)
+    void* peerImage[2][IDK_MAX_PEERS] = {};                               // mapped peers (own entries = own buffers)
+    void* peerFlags[2][IDK_MAX_PEERS] = {};
+    bool peerMapped[IDK_MAX_PEERS] = {};
+    uint32_t gatherEpoch = 0;
+    int gatherCurrent = -1;                                               // buffer holding the last completed frame
+
     // asynchronous presentation (device snapshot + D2H on a second stream, overlapping the next Compute)
     cudaStream_t copyStream = nullptr;
     cudaEvent_t snapDone = nullptr, copyDone = nullptr;
@@ -321,6 +330,15 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ctx->sortScratch);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
+    for (int b = 0; b < 2; b++)
+        for (int p = 0; p < IDK_MAX_PEERS; p++)
+            if (ctx->peerMapped[p] && p != ctx->gatherRank) {
+                if (ctx->peerImage[b][p]) cudaIpcCloseMemHandle(ctx->peerImage[b][p]);
+                if (ctx->peerFlags[b][p]) cudaIpcCloseMemHandle(ctx->peerFlags[b][p]);
+            }
+    for (int b = 0; b < 2; b++) { release(ctx->gatherImage[b]); release(ctx->gatherFlags[b]); }
+    release(ctx->gatherRows);
+    release(ctx->gatherScratch);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->snapDone) cudaEventDestroy(ctx->snapDone);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
@@ -737,12 +755,34 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
         }
 
         e0 = ev.begin();
-        k_accumulate<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ctx->radiance.p, (const float4*)ctx->aovAlbedoFinal.p,
-                                                               (const float4*)ctx->aovNormalFinal.p, (float4*)ctx->images[0].p,
-                                                               (float4*)ctx->images[1].p, (float4*)ctx->images[2].p, n,
-                                                               ctx->accumulatedSamples, st->Gpu.DoDebugBVHTraversal, aovs ? 1 : 0);
+        const bool gatherNow = ctx->gatherWorld > 1 && s == st->SamplesPerPixel - 1;
+        if (gatherNow) {
+            // FinalDraw fused with the all-gather: Result pixels go straight to every rank's full image over NVLink
+            const int b = (int)((ctx->gatherEpoch + 1) & 1u);
+            GatherArgs g;
+            memset(&g, 0, sizeof(g));
+            for (int p = 0; p < ctx->gatherWorld; p++) { g.peerImage[p] = (float4*)ctx->peerImage[b][p]; g.peerFlags[p] = (uint32_t*)ctx->peerFlags[b][p]; }
+            g.tileRows = (const int*)ctx->gatherRows.p;
+            g.doneCounter = (uint32_t*)ctx->gatherScratch.p;
+            g.world = ctx->gatherWorld; g.rank = ctx->gatherRank; g.width = ctx->width;
+            g.epoch = ++ctx->gatherEpoch;
+            CK(cudaMemsetAsync(ctx->gatherScratch.p, 0, 8, ctx->stream));
+            k_accumulate_scatter<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ctx->radiance.p, (float4*)ctx->images[0].p, n,
+                                                                           ctx->accumulatedSamples, st->Gpu.DoDebugBVHTraversal, g);
+            if (aovs)   // AOV images stay local to the tile (only Result is gathered)
+                k_accumulate_aov<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ctx->aovAlbedoFinal.p, (const float4*)ctx->aovNormalFinal.p,
+                                                                           (float4*)ctx->images[1].p, (float4*)ctx->images[2].p, n, ctx->accumulatedSamples);
+            k_gather_wait<<<1, 32, 0, ctx->stream>>>((const uint32_t*)ctx->gatherFlags[b].p, ctx->gatherWorld, g.epoch, (uint32_t*)ctx->gatherScratch.p + 1);
+            ctx->gatherCurrent = b;
+            launches += aovs ? 3 : 2;
+        } else {
+            k_accumulate<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ctx->radiance.p, (const float4*)ctx->aovAlbedoFinal.p,
+                                                                   (const float4*)ctx->aovNormalFinal.p, (float4*)ctx->images[0].p,
+                                                                   (float4*)ctx->images[1].p, (float4*)ctx->images[2].p, n,
+                                                                   ctx->accumulatedSamples, st->Gpu.DoDebugBVHTraversal, aovs ? 1 : 0);
+            launches++;
+        }
         ev.end(e0, 3);
-        launches++;
         if (stats) CK(cudaMemcpyAsync((uint32_t*)countLog.p + (size_t)s * (IDKPT_MAX_RAY_DEPTH + 1), counts,
                                       (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->accumulatedSamples++;   // PathTracer.cs:269
@@ -755,6 +795,11 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
         return IDKPT_ERR_CUDA;
     }
 
+    if (ctx->gatherWorld > 1) {
+        uint32_t timedOut = 0;
+        CK(cudaMemcpy(&timedOut, (uint32_t*)ctx->gatherScratch.p + 1, 4, cudaMemcpyDeviceToHost));
+        if (timedOut) return fail(ctx, IDKPT_ERR_CUDA, "idkpt_compute: timed out waiting for a peer rank's tile (multi-GPU gather)");
+    }
     if (stats) {
         CK(cudaMemcpy(hostCounts.data(), countLog.p, hostCounts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
         for (int s = 0; s < st->SamplesPerPixel; s++)
@@ -817,9 +862,25 @@ IDKPT_API int idkpt_write_result(IdkPtCtx* ctx, IdkPtImage which, const void* sr
 // and copy the snapshot to (ideally pinned) host memory on a second stream, so the transfer overlaps the next Compute.
 IDKPT_API int idkpt_present_async(IdkPtCtx* ctx, IdkPtImage which, void* dstHost, uint64_t bytes) {
     if (!ctx || !dstHost) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: null argument");
-    if ((int)which < 0 || (int)which > 2) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: unknown image");
+    if ((int)which < 0 || (int)which > 3) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: unknown image");
     if (bytes < (uint64_t)ctx->width * ctx->height * 16) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: buffer smaller than width*height*16");
     CK(cudaSetDevice(ctx->device));
+    if ((int)which == 3) {
+        // IDKPT_IMAGE_GATHERED: the full multi-GPU frame. The gather buffers are double-buffered, so the transfer can read
+        // the buffer directly while the next idkpt_compute fills the other one.
+        if (ctx->gatherWorld < 2 || ctx->gatherCurrent < 0) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: no gathered frame yet");
+        if (!ctx->copyStream) {
+            CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+            CK(cudaEventCreateWithFlags(&ctx->snapDone, cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming));
+        }
+        CK(cudaEventRecord(ctx->snapDone, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->copyStream, ctx->snapDone, 0));
+        CK(cudaMemcpyAsync(dstHost, ctx->gatherImage[ctx->gatherCurrent].p, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDeviceToHost, ctx->copyStream));
+        CK(cudaEventRecord(ctx->copyDone, ctx->copyStream));
+        ctx->copyPending = true;
+        return IDKPT_OK;
+    }
     if (!ctx->copyStream) {
         CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
         CK(cudaEventCreateWithFlags(&ctx->snapDone, cudaEventDisableTiming));
@@ -852,6 +913,69 @@ IDKPT_API int idkpt_present_wait(IdkPtCtx* ctx) {
         CK(cudaEventSynchronize(ctx->copyDone));
         ctx->copyPending = false;
     }
+    return IDKPT_OK;
+}
+
+// ---- multi-GPU gather over peer memory -----------------------------------------------------------------------------
+// Step 1 (every rank): allocate the exported buffers and return their CUDA IPC handles (4 x 64 bytes:
+// image[0], image[1], flags[0], flags[1]). Step 2: exchange the handles (any transport) and import all ranks' handles.
+IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handlesOut, uint64_t bytes) {
+    if (!ctx || !handlesOut) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_export: null argument");
+    if (bytes < 4 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_export: need 256 bytes");
+    CK(cudaSetDevice(ctx->device));
+    const size_t imgBytes = (size_t)ctx->width * ctx->height * 16;
+    cudaIpcMemHandle_t* out = (cudaIpcMemHandle_t*)handlesOut;
+    for (int b = 0; b < 2; b++) {
+        // IPC export needs stand-alone cudaMalloc allocations
+        CK(ensure(ctx->gatherImage[b], imgBytes));
+        CK(ensure(ctx->gatherFlags[b], IDK_MAX_PEERS * sizeof(uint32_t)));
+        CK(cudaMemsetAsync(ctx->gatherImage[b].p, 0, imgBytes, ctx->stream));
+        CK(cudaMemsetAsync(ctx->gatherFlags[b].p, 0, IDK_MAX_PEERS * sizeof(uint32_t), ctx->stream));
+        CK(cudaIpcGetMemHandle(&out[b], ctx->gatherImage[b].p));
+        CK(cudaIpcGetMemHandle(&out[2 + b], ctx->gatherFlags[b].p));
+    }
+    CK(ensure(ctx->gatherScratch, 16));
+    CK(cudaMemsetAsync(ctx->gatherScratch.p, 0, 16, ctx->stream));
+    CK(ensure(ctx->gatherRows, std::max<size_t>(ctx->rows.size(), 1) * sizeof(int)));
+    if (!ctx->rows.empty()) CK(cudaMemcpyAsync(ctx->gatherRows.p, ctx->rows.data(), ctx->rows.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IDKPT_OK;
+}
+
+// allHandles = world x 256 bytes in rank order (this rank's own entry is ignored and replaced by the local pointers).
+IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, const void* allHandles, uint64_t bytes) {
+    if (!ctx || !allHandles) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: null argument");
+    if (world < 2 || world > IDK_MAX_PEERS || rank < 0 || rank >= world) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: invalid rank / world");
+    if (world != ctx->tileCount || rank != ctx->tileIndex) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: rank / world must equal TileIndex / TileCount");
+    if (bytes < (uint64_t)world * 4 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: handle buffer too small");
+    if (!ctx->gatherImage[0].p) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: call idkpt_gather_export first");
+    CK(cudaSetDevice(ctx->device));
+    const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)allHandles;
+    for (int p = 0; p < world; p++) {
+        for (int b = 0; b < 2; b++) {
+            if (p == rank) {
+                ctx->peerImage[b][p] = ctx->gatherImage[b].p;
+                ctx->peerFlags[b][p] = ctx->gatherFlags[b].p;
+            } else {
+                CK(cudaIpcOpenMemHandle(&ctx->peerImage[b][p], hs[4 * p + b], cudaIpcMemLazyEnablePeerAccess));
+                CK(cudaIpcOpenMemHandle(&ctx->peerFlags[b][p], hs[4 * p + 2 + b], cudaIpcMemLazyEnablePeerAccess));
+            }
+        }
+        ctx->peerMapped[p] = true;
+    }
+    ctx->gatherWorld = world;
+    ctx->gatherRank = rank;
+    ctx->gatherEpoch = 0;
+    ctx->gatherCurrent = -1;
+    return IDKPT_OK;
+}
+
+// Full image (all ranks' tiles) of the last idkpt_compute; valid until the compute after next (double-buffered).
+IDKPT_API int idkpt_gather_device_ptr(IdkPtCtx* ctx, void** devPtr, uint64_t* bytes) {
+    if (!ctx || !devPtr) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_device_ptr: null argument");
+    if (ctx->gatherWorld < 2 || ctx->gatherCurrent < 0) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_device_ptr: no gathered frame yet");
+    *devPtr = ctx->gatherImage[ctx->gatherCurrent].p;
+    if (bytes) *bytes = (uint64_t)ctx->width * ctx->height * 16;
     return IDKPT_OK;
 }
 

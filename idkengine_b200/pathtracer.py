@@ -135,6 +135,21 @@ class PathTracer:
     def PresentWait(self):
         self._check(self._lib.idkpt_present_wait(self._ctx), "idkpt_present_wait")
 
+    def EnablePeerGather(self, rank, world, exchange):
+        """Multi-GPU: fuse the tile all-gather into Compute() over NVLink peer memory. `exchange(bytes) -> list[bytes]`
+        must return every rank's blob in rank order (e.g. torch.distributed.all_gather_object)."""
+        buf = (ctypes.c_uint8 * capi.IDKPT_GATHER_HANDLE_BYTES)()
+        self._check(self._lib.idkpt_gather_export(self._ctx, buf, len(buf)), "idkpt_gather_export")
+        blobs = exchange(bytes(buf))
+        assert len(blobs) == world and all(len(b) == capi.IDKPT_GATHER_HANDLE_BYTES for b in blobs)
+        allh = (ctypes.c_uint8 * (world * capi.IDKPT_GATHER_HANDLE_BYTES)).from_buffer_copy(b"".join(blobs))
+        self._check(self._lib.idkpt_gather_import(self._ctx, rank, world, allh, len(allh)), "idkpt_gather_import")
+
+    def GatheredDevicePtr(self):
+        p, n = ctypes.c_void_p(), ctypes.c_uint64()
+        self._check(self._lib.idkpt_gather_device_ptr(self._ctx, ctypes.byref(p), ctypes.byref(n)), "idkpt_gather_device_ptr")
+        return p.value, n.value
+
     def ResultDevicePtr(self, which=capi.IDKPT_IMAGE_RESULT):
         p, n = ctypes.c_void_p(), ctypes.c_uint64()
         self._check(self._lib.idkpt_result_device_ptr(self._ctx, which, ctypes.byref(p), ctypes.byref(n)), "idkpt_result_device_ptr")

@@ -129,7 +129,8 @@ typedef struct IdkPtStats {
 typedef enum IdkPtImage {
     IDKPT_IMAGE_RESULT = 0,   /* PathTracer.Result        (PathTracer.cs:143) */
     IDKPT_IMAGE_ALBEDO = 1,   /* PathTracer.AlbedoTexture (PathTracer.cs:167) */
-    IDKPT_IMAGE_NORMAL = 2    /* PathTracer.NormalTexture (PathTracer.cs:168) */
+    IDKPT_IMAGE_NORMAL = 2,   /* PathTracer.NormalTexture (PathTracer.cs:168) */
+    IDKPT_IMAGE_GATHERED = 3  /* full multi-GPU Result (idkpt_present_async only; needs idkpt_gather_import) */
 } IdkPtImage;
 
 /* One ray / hit record of the stand-alone closest-hit query (the GPU analogue of
@@ -181,6 +182,16 @@ IDKPT_API int idkpt_write_result(IdkPtCtx* ctx, IdkPtImage which, const void* sr
  * most recent transfer has landed. The GL-free analogue of handing Result to the presenter each frame. */
 IDKPT_API int idkpt_present_async(IdkPtCtx* ctx, IdkPtImage which, void* dst_rgba32f_host, uint64_t bytes);
 IDKPT_API int idkpt_present_wait(IdkPtCtx* ctx);
+
+/* Multi-GPU tile gather over NVLink peer memory (no NCCL in the data path). Every rank calls idkpt_gather_export
+ * (allocates a double-buffered full-size image + arrival flags and returns 4 CUDA IPC handles = 256 bytes), the ranks
+ * exchange the handles (torch.distributed, MPI, a socket...) and call idkpt_gather_import with all of them in rank
+ * order. From then on the FinalDraw of every idkpt_compute also stores this rank's pixels into every rank's full image
+ * at their final position and idkpt_compute returns once all ranks' tiles of that frame have arrived. */
+#define IDKPT_GATHER_HANDLE_BYTES 256
+IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handles_out, uint64_t bytes);
+IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, const void* all_handles, uint64_t bytes);
+IDKPT_API int idkpt_gather_device_ptr(IdkPtCtx* ctx, void** dev_ptr, uint64_t* bytes);
 
 /* Device-side access for zero-copy hand-over (GL interop / NCCL gather):
  * pointer to this tile's compact rgba32f rows (TileRowCount*Width float4). */
