@@ -1,11 +1,14 @@
 // Wavefront path-tracing kernels for sm_100a (B200). See DESIGN.md for the HBM layout and the
 // algorithmic-byte accounting of each kernel.
 //
-//   k_prepare_triangles  scene upload: 48-byte triangle records (p0,e1,e2,n) from indices+positions
+//   k_prepare_triangles/vertices/surfaces  scene upload: 48-byte triangle records, decoded vertex frames, per-mesh surfaces
+//   k_init_sample        per sample: zero alive counts and work tickets
 //   k_raygen             FirstHit/compute.glsl:44-81   ray generation (camera, jitter, thin lens)
-//   k_traverse           BVHIntersect.glsl:27-105,183-291  closest hit, persistent warps + dynamic fetch
-//   k_shade              FirstHit/compute.glsl:100-234, NHit/compute.glsl:91-215 + ordered compaction
-//   k_accumulate         FinalDraw/compute.glsl:24-62
+//   k_traverse           BVHIntersect.glsl:27-105,183-291  closest hit, one ray per lane (primary rays, TLAS walk)
+//   k_traverse2          same per-ray operation sequence, warp-level SETUP/BOX/LEAF phase scheduling with lane refill
+//   k_shade              FirstHit/compute.glsl:100-234, NHit/compute.glsl:91-215 (barrier-free, state in place)
+//   k_compact            the ordered (canonical) outcome of the alive-list atomics, decoupled look-back scan
+//   k_accumulate         FinalDraw/compute.glsl:24-62; k_accumulate_scatter: fused with the NVLink peer gather
 //   k_trace_rays         stand-alone closest-hit batch (BVH.Intersect analogue)
 #pragma once
 #include "idk_device.cuh"

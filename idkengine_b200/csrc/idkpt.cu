@@ -261,6 +261,25 @@ static int relayout_treelet(const GpuBlasNode* src, uint32_t nodeCount, uint32_t
     return (int)inTreelet;
 }
 
+static void gather_teardown(IdkPtCtx* ctx) {
+    for (int b = 0; b < 2; b++)
+        for (int p = 0; p < IDK_MAX_PEERS; p++) {
+            if (ctx->peerMapped[p] && p != ctx->gatherRank) {
+                if (ctx->peerImage[b][p]) cudaIpcCloseMemHandle(ctx->peerImage[b][p]);
+                if (ctx->peerFlags[b][p]) cudaIpcCloseMemHandle(ctx->peerFlags[b][p]);
+            }
+            ctx->peerImage[b][p] = nullptr;
+            ctx->peerFlags[b][p] = nullptr;
+        }
+    for (int p = 0; p < IDK_MAX_PEERS; p++) ctx->peerMapped[p] = false;
+    for (int b = 0; b < 2; b++) { release(ctx->gatherImage[b]); release(ctx->gatherFlags[b]); }
+    release(ctx->gatherRows);
+    release(ctx->gatherScratch);
+    ctx->gatherWorld = 0;
+    ctx->gatherCurrent = -1;
+    ctx->gatherEpoch = 0;
+}
+
 extern "C" {
 
 IDKPT_API uint32_t idkpt_abi_version(void) { return IDKPT_ABI_VERSION; }
@@ -330,15 +349,7 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ctx->sortScratch);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
-    for (int b = 0; b < 2; b++)
-        for (int p = 0; p < IDK_MAX_PEERS; p++)
-            if (ctx->peerMapped[p] && p != ctx->gatherRank) {
-                if (ctx->peerImage[b][p]) cudaIpcCloseMemHandle(ctx->peerImage[b][p]);
-                if (ctx->peerFlags[b][p]) cudaIpcCloseMemHandle(ctx->peerFlags[b][p]);
-            }
-    for (int b = 0; b < 2; b++) { release(ctx->gatherImage[b]); release(ctx->gatherFlags[b]); }
-    release(ctx->gatherRows);
-    release(ctx->gatherScratch);
+    gather_teardown(ctx);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
     if (ctx->snapDone) cudaEventDestroy(ctx->snapDone);
     if (ctx->copyDone) cudaEventDestroy(ctx->copyDone);
@@ -560,6 +571,7 @@ IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height) {
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->copyPending) { CK(cudaEventSynchronize(ctx->copyDone)); ctx->copyPending = false; }
+    gather_teardown(ctx);   // the exported full-frame buffers have the old size: peers must export / import again
     ctx->width = width;
     ctx->height = height;
     compute_tile_rows(ctx);

@@ -187,7 +187,8 @@ IDKPT_API int idkpt_present_wait(IdkPtCtx* ctx);
  * (allocates a double-buffered full-size image + arrival flags and returns 4 CUDA IPC handles = 256 bytes), the ranks
  * exchange the handles (torch.distributed, MPI, a socket...) and call idkpt_gather_import with all of them in rank
  * order. From then on the FinalDraw of every idkpt_compute also stores this rank's pixels into every rank's full image
- * at their final position and idkpt_compute returns once all ranks' tiles of that frame have arrived. */
+ * at their final position and idkpt_compute returns once all ranks' tiles of that frame have arrived (or fails after
+ * ~3 s if a peer never delivers). idkpt_resize drops the mappings: export / exchange / import again afterwards. */
 #define IDKPT_GATHER_HANDLE_BYTES 256
 IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handles_out, uint64_t bytes);
 IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, const void* all_handles, uint64_t bytes);

@@ -362,3 +362,18 @@ def test_resize_and_snapshot_restore(cornell):
         pt.Compute()
         o = ol.path_trace(scene, scenes.camera_frame(cam, 96, 48), s, 96, 48, sky=(0, 0, 0))
         assert feq(pt.Result, o.result)
+
+
+def test_multi_gpu_peer_gather():
+    """Fused FinalDraw + NVLink peer-memory gather vs NCCL all-gather vs per-tile oracle (needs >= 2 GPUs; the single-GPU
+    driver box skips it, scripts/gpu_multi.sh runs the same script under gpurun --gpus N)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29541", os.path.join(repo, "scripts", "check_peer_gather.py")], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0 and "PEER_GATHER_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
