@@ -13,6 +13,7 @@
 
 #define IDKVX_MAX_LEVELS 16
 #define IDKVX_SMALL_LIMIT 16   // bounding boxes up to this many pixel centres are rasterised by the discovering thread
+#define IDKVX_TILE 64          // larger boxes are cut into IDKVX_TILE^2 pixel tiles, one CTA each
 
 struct VxGridDev {
     unsigned long long* level[IDKVX_MAX_LEVELS];   // 4 x half per texel
@@ -163,8 +164,9 @@ struct VxVoxelizeArgs {
     VxGridDev g;
     uint32_t instance;
     uint32_t triFirst, triCount;     // BlasTriangles range of this instance's BLAS
-    uint2* queue;                    // (instance, triangle) of large triangles
+    uint4* queue;                    // (instance, triangle, tile x, tile y) work items of large triangles
     uint32_t* queueCount;
+    uint32_t queueCapacity;
     unsigned long long* fragments;
 };
 
@@ -180,8 +182,20 @@ __global__ void __launch_bounds__(256) k_vx_voxelize_small(VxVoxelizeArgs a) {
                 for (int j = t.j0; j <= t.j1; j++)
                     for (int i = t.i0; i <= t.i1; i++) frags += vx_pixel(a.sc, a.g, t, i, j) ? 1u : 0u;
             } else {
-                const uint32_t slot = atomicAdd(a.queueCount, 1u);
-                a.queue[slot] = make_uint2(a.instance, a.triFirst + k);
+                // cut the bounding box into tiles and queue one work item per tile (a wall-sized triangle becomes
+                // dozens of CTAs instead of one); if the queue is full the thread rasterises the remainder itself
+                const int tx = (t.i1 - t.i0) / IDKVX_TILE + 1, ty = (t.j1 - t.j0) / IDKVX_TILE + 1;
+                const uint32_t slot = atomicAdd(a.queueCount, (uint32_t)(tx * ty));
+                for (int q = 0; q < tx * ty; q++) {
+                    const int ox = q % tx, oy = q / tx;
+                    if (slot + (uint32_t)q < a.queueCapacity) {
+                        a.queue[slot + q] = make_uint4(a.instance, a.triFirst + k, (uint32_t)ox, (uint32_t)oy);
+                    } else {
+                        const int i0 = t.i0 + ox * IDKVX_TILE, j0 = t.j0 + oy * IDKVX_TILE;
+                        for (int j = j0; j <= min(t.j1, j0 + IDKVX_TILE - 1); j++)
+                            for (int i = i0; i <= min(t.i1, i0 + IDKVX_TILE - 1); i++) frags += vx_pixel(a.sc, a.g, t, i, j) ? 1u : 0u;
+                    }
+                }
             }
         }
     }
@@ -189,18 +203,20 @@ __global__ void __launch_bounds__(256) k_vx_voxelize_small(VxVoxelizeArgs a) {
     if ((threadIdx.x & 31) == 0 && frags) atomicAdd(a.fragments, (unsigned long long)frags);
 }
 
-// one block per large triangle, threads stride over the bounding box
-__global__ void __launch_bounds__(256) k_vx_voxelize_large(VxScene sc, VxGridDev g, const uint2* __restrict__ queue,
-                                                           const uint32_t* __restrict__ queueCount, unsigned long long* fragments) {
-    const uint32_t n = *queueCount;
+// one CTA per queued (triangle, tile) work item, threads stride over the tile's pixel centres
+__global__ void __launch_bounds__(256) k_vx_voxelize_large(VxScene sc, VxGridDev g, const uint4* __restrict__ queue,
+                                                           const uint32_t* __restrict__ queueCount, uint32_t queueCapacity,
+                                                           unsigned long long* fragments) {
+    const uint32_t n = min(*queueCount, queueCapacity);
     uint32_t frags = 0;
     for (uint32_t q = blockIdx.x; q < n; q += gridDim.x) {
-        const uint2 e = queue[q];
+        const uint4 e = queue[q];
         VxTri t;
         vx_setup(sc, g, e.x, e.y, t);
-        const int w = t.i1 - t.i0 + 1, h = t.j1 - t.j0 + 1;
+        const int i0 = t.i0 + (int)e.z * IDKVX_TILE, j0 = t.j0 + (int)e.w * IDKVX_TILE;
+        const int w = min(t.i1, i0 + IDKVX_TILE - 1) - i0 + 1, h = min(t.j1, j0 + IDKVX_TILE - 1) - j0 + 1;
         for (int p = threadIdx.x; p < w * h; p += blockDim.x)
-            frags += vx_pixel(sc, g, t, t.i0 + p % w, t.j0 + p / w) ? 1u : 0u;
+            frags += vx_pixel(sc, g, t, i0 + p % w, j0 + p / w) ? 1u : 0u;
     }
     for (int off = 16; off > 0; off >>= 1) frags += __shfl_down_sync(0xffffffffu, frags, off);
     if ((threadIdx.x & 31) == 0 && frags) atomicAdd(fragments, (unsigned long long)frags);

@@ -261,6 +261,35 @@ static int relayout_treelet(const GpuBlasNode* src, uint32_t nodeCount, uint32_t
     return (int)inTreelet;
 }
 
+// Structural validation of one BLAS before its arrays reach the kernels (a malformed host array must become an error
+// code, never a device fault): child pairs in range, even, and behind their parent (the builder emits DFS order, which
+// also rules out cycles); leaf ranges inside the BLAS's triangle range; and the traversal stack the kernels will need
+// (BLAS.ComputeRequiredStackSize, Bvh/BLAS.cs:672-702) must fit BlasStackSize. Returns nullptr or an error text.
+static const char* validate_blas(const GpuBlasNode* nodes, const GpuBlasDesc& d, int blasStackSize) {
+    const int n = d.NodeCount;
+    if (n < 4 || (n & 1)) return "idkpt_set_scene: BLAS node count must be even and >= 4";
+    if (nodes[1].TriCount != 0 || nodes[1].TriStartOrChild != 2) return "idkpt_set_scene: BLAS root must be interior with children at 2 (BLAS.cs:16-22)";
+    std::vector<int> req((size_t)n / 2, 0);
+    for (int p = n / 2 - 1; p >= 1; p--) {
+        int need[2] = {-1, -1};
+        for (int c = 0; c < 2; c++) {
+            const GpuBlasNode& nd = nodes[2 * p + c];
+            if (nd.TriCount > 0) {
+                if (nd.TriStartOrChild < 0 || (int64_t)nd.TriStartOrChild + nd.TriCount > d.TriangleCount) return "idkpt_set_scene: BLAS leaf triangle range outside the BLAS";
+            } else if (nd.TriCount == 0) {
+                const int ch = nd.TriStartOrChild;
+                if (ch <= 2 * p || (ch & 1) || ch + 1 >= n) return "idkpt_set_scene: BLAS child index out of range / not in DFS order";
+                need[c] = req[(size_t)ch / 2];
+            } else {
+                return "idkpt_set_scene: negative TriCount in a BLAS node";
+            }
+        }
+        req[p] = (need[0] >= 0 && need[1] >= 0) ? std::max(need[0], need[1]) + 1 : std::max(need[0], std::max(need[1], 0));
+    }
+    if (req[1] > blasStackSize) return "idkpt_set_scene: BlasStackSize smaller than the traversal stack this BLAS needs";
+    return nullptr;
+}
+
 static void gather_teardown(IdkPtCtx* ctx) {
     for (int b = 0; b < 2; b++)
         for (int p = 0; p < IDK_MAX_PEERS; p++) {
@@ -388,6 +417,7 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
             return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuBlasDesc range outside the node/triangle arrays");
         if (d.RequiredStackSize > s->BlasStackSize)
             return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: BlasStackSize smaller than a BLAS's RequiredStackSize");
+        if (const char* err = validate_blas(s->BlasNodes + d.NodeOffset, d, s->BlasStackSize)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, err);
     }
     for (uint64_t i = 0; i < s->MeshCount; i++)
         if (s->Meshes[i].MaterialId < 0 || (uint64_t)s->Meshes[i].MaterialId >= s->MaterialCount)

@@ -170,8 +170,8 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
     ctx->hostInstances.assign(s->BlasInstances, s->BlasInstances + s->BlasInstanceCount);
     for (const GpuBlasInstance& bi : ctx->hostInstances) maxTris += (size_t)ctx->hostDescs[bi.BlasId].TriangleCount;
     if (ctx->dQueue) { cudaFree(ctx->dQueue); ctx->dQueue = nullptr; }
-    VCK(cudaMalloc(&ctx->dQueue, std::max<size_t>(maxTris, 1) * sizeof(uint2)));
-    ctx->queueCapacity = maxTris;
+    ctx->queueCapacity = maxTris * 2 + (1u << 20);   // (triangle, tile) work items of large triangles
+    VCK(cudaMalloc(&ctx->dQueue, ctx->queueCapacity * sizeof(uint4)));
     VxScene& sc = ctx->sc;
     sc.positions = (const float*)ctx->dPositions;
     sc.vertices = (const uint4*)ctx->dVertices;
@@ -209,12 +209,13 @@ IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats) {
         VxVoxelizeArgs a;
         a.sc = ctx->sc; a.g = ctx->grid; a.instance = (uint32_t)i;
         a.triFirst = (uint32_t)d.TriangleOffset; a.triCount = (uint32_t)d.TriangleCount;
-        a.queue = (uint2*)ctx->dQueue; a.queueCount = (uint32_t*)ctx->dQueueCount; a.fragments = (unsigned long long*)ctx->dCounters;
+        a.queue = (uint4*)ctx->dQueue; a.queueCount = (uint32_t*)ctx->dQueueCount; a.queueCapacity = (uint32_t)ctx->queueCapacity;
+        a.fragments = (unsigned long long*)ctx->dCounters;
         k_vx_voxelize_small<<<(a.triCount + 255) / 256, 256, 0, ctx->stream>>>(a);
         launches++;
     }
-    k_vx_voxelize_large<<<ctx->smCount * 4, 256, 0, ctx->stream>>>(ctx->sc, ctx->grid, (const uint2*)ctx->dQueue, (const uint32_t*)ctx->dQueueCount,
-                                                                     (unsigned long long*)ctx->dCounters);
+    k_vx_voxelize_large<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->sc, ctx->grid, (const uint4*)ctx->dQueue, (const uint32_t*)ctx->dQueueCount,
+                                                                     (uint32_t)ctx->queueCapacity, (unsigned long long*)ctx->dCounters);
     launches++;
     VCK(cudaEventRecord(ev[2], ctx->stream));
     for (int l = 1; l < ctx->grid.levels; l++) {

@@ -287,6 +287,16 @@ def test_errors(cornell):
         bad.blas_descs["NodeCount"][0] += 1000
         with pytest.raises(IdkPtError, match="GpuBlasDesc range"):
             pt.SetScene(bad)
+        bad = scenes.cornell_1k(threads=1)[0]
+        interior = [i for i in range(10, len(bad.blas_nodes)) if bad.blas_nodes["TriCount"][i] == 0][0]
+        bad.blas_nodes["TriStartOrChild"][interior] = 4        # points back up the tree: a cycle
+        with pytest.raises(IdkPtError, match="DFS order|child index"):
+            pt.SetScene(bad)
+        bad = scenes.cornell_1k(threads=1)[0]
+        bad.blas_stack_size = 3                                # smaller than the tree needs
+        bad.blas_descs["RequiredStackSize"][0] = 3
+        with pytest.raises(IdkPtError, match="traversal stack"):
+            pt.SetScene(bad)
     with pytest.raises(IdkPtError, match="device ordinal"):
         PathTracer(32, 32, device=99)
 
