@@ -70,6 +70,7 @@ class IdkPtStats(ctypes.Structure):
 IDKPT_IMAGE_RESULT, IDKPT_IMAGE_ALBEDO, IDKPT_IMAGE_NORMAL, IDKPT_IMAGE_GATHERED = 0, 1, 2, 3
 IDKPT_GATHER_HANDLE_BYTES = 256
 IDKPT_ARRAY_MESH_TRANSFORMS, IDKPT_ARRAY_MESHES, IDKPT_ARRAY_MATERIALS, IDKPT_ARRAY_LIGHTS = 0, 1, 2, 3
+IDKPT_ARRAY_TLAS_NODES, IDKPT_ARRAY_BLAS_NODES, IDKPT_ARRAY_VERTEX_POSITIONS, IDKPT_ARRAY_VERTICES = 4, 5, 6, 7
 
 # every symbol include/idkpt.h declares
 EXPORTS = [
@@ -78,7 +79,8 @@ EXPORTS = [
     "idkpt_compute", "idkpt_read_result", "idkpt_write_result", "idkpt_present_async", "idkpt_present_wait",
     "idkpt_gather_export", "idkpt_gather_import", "idkpt_gather_device_ptr",
     "idkpt_result_device_ptr", "idkpt_tile_rows",
-    "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_abi_version",
+    "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_trace_rays_any", "idkpt_shadows_ray_traced",
+    "idkpt_set_skinning_data", "idkpt_skin_vertices", "idkpt_blas_refit", "idkpt_read_range", "idkpt_abi_version",
 ]
 
 
@@ -199,6 +201,18 @@ def load(path=None):
     L.idkpt_read_wavefront_rays.argtypes = [c_vp, c_vp, c_u64]
     L.idkpt_trace_rays.restype = c_i32
     L.idkpt_trace_rays.argtypes = [c_vp, c_vp, c_u64, c_i32, c_vp, P(c_f)]
+    L.idkpt_trace_rays_any.restype = c_i32
+    L.idkpt_trace_rays_any.argtypes = [c_vp, c_vp, c_u64, c_i32, c_vp, P(c_f)]
+    L.idkpt_shadows_ray_traced.restype = c_i32
+    L.idkpt_shadows_ray_traced.argtypes = [c_vp, c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, c_u32, c_vp, c_vp, P(c_f)]
+    L.idkpt_set_skinning_data.restype = c_i32
+    L.idkpt_set_skinning_data.argtypes = [c_vp, c_vp, c_u64]
+    L.idkpt_skin_vertices.restype = c_i32
+    L.idkpt_skin_vertices.argtypes = [c_vp, c_vp, c_u64, c_vp, c_u32, P(c_f)]
+    L.idkpt_blas_refit.restype = c_i32
+    L.idkpt_blas_refit.argtypes = [c_vp, c_u32, c_u32, P(c_f)]
+    L.idkpt_read_range.restype = c_i32
+    L.idkpt_read_range.argtypes = [c_vp, c_i32, c_u64, c_u64, c_vp]
     L.idkpt_abi_version.restype = c_u32
     L.idkpt_abi_version.argtypes = []
     if path == _build.LIBIDKPT:

@@ -70,6 +70,19 @@ __device__ __forceinline__ float det_exp(float x) {
     return e * __int_as_float((n + 127) << 23);
 }
 
+// ---- deterministic log2: Cephes logf polynomial on [sqrt(1/2), sqrt(2)), then * log2(e) + exponent
+__device__ __forceinline__ float det_log2(float x) {
+    const uint32_t bits = __float_as_uint(x);
+    int e = (int)((bits >> 23) & 255u) - 126;
+    float m = __uint_as_float((bits & 0x807FFFFFu) | 0x3F000000u);
+    if (m < 0.70710678f) { m = m + m; e -= 1; }
+    m = m - 1.0f;
+    const float z = m * m;
+    float y = ((((((((7.0376836292e-2f * m - 1.1514610310e-1f) * m + 1.1676998740e-1f) * m - 1.2420140846e-1f) * m + 1.4249322787e-1f) * m - 1.6668057665e-1f) * m + 2.0000714765e-1f) * m - 2.4999993993e-1f) * m + 3.3333331174e-1f) * m * z;
+    y = y - 0.5f * z;
+    return (m + y) * 1.44269504f + (float)e;
+}
+
 // ---- RNG (Random.glsl:16-33)
 __device__ __forceinline__ uint32_t pcg_hash(uint32_t& seed) {
     seed = seed * 747796405u + 2891336453u;

@@ -13,6 +13,9 @@
 #include "../../include/idkpt.h"
 #include "idk_kernels.cuh"
 #include "idk_sort.cuh"
+#include "idk_shadows.cuh"
+#include "idk_dynamic.cuh"
+#include "idk_post.cuh"
 
 #define IDKPT_ABI_VERSION 1u
 
@@ -44,6 +47,16 @@ struct IdkPtCtx {
     float sky[3] = {0.0f, 0.0f, 0.0f};
     DevBuf skyFaces;
     int skyFaceSize = 0;
+
+    // present chain: bloom mip chains (rgba16f), AgX constants, RGBA8 frame
+    DevBuf bloomDown, bloomUp, postConsts, ldr;
+
+    // dynamic geometry: unskinned vertices, joint matrices, refit scratch (parents + locks of the largest BLAS)
+    DevBuf unskinned, joints, refitParents, refitLocks;
+    uint64_t unskinnedCount = 0;
+    std::vector<uint32_t> unskinnedMaxJoint;   // per vertex max(JointIndices), host copy for range validation
+    std::vector<GpuBlasDesc> hostDescs;
+    size_t nodeBytes = 0;
 
     // wavefront buffers
     DevBuf state, aov, alive[2], survivors, keysTmp, sortedAlive, hits, hitXform, debugCost, radiance, aovAlbedoFinal, aovNormalFinal;
@@ -139,6 +152,8 @@ static int configure_launches(IdkPtCtx* ctx) {
     CK(cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
+    CK(cudaFuncSetAttribute(k_trace_rays_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
+    CK(cudaFuncSetAttribute(k_shadows_ray_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     ctx->traverse2Smem = ctx->stackBytes + (size_t)ctx->treeletNodes * 32;
     CK(cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
     CK(cudaFuncSetAttribute(k_traverse2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
@@ -506,6 +521,8 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     sc.vtxFrame = (const float4*)ctx->vtxFrame.p;
     sc.surfRec = (const float4*)ctx->surfRec.p;
     ctx->counts = *s;
+    ctx->hostDescs.assign(s->BlasDescs, s->BlasDescs + s->BlasDescCount);
+    ctx->nodeBytes = nodeBytes;
     if ((rc = configure_launches(ctx))) return rc;
     // Keep the BVH resident in the 126 MB L2: persisting access-policy window over [nodes | triRec] on the render stream.
     // The wavefront buffers (hundreds of MB per frame) stream through the rest of the cache without evicting the tree.
@@ -549,6 +566,7 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
         case IDKPT_ARRAY_MESHES: b = &ctx->meshes; elem = sizeof(GpuMesh); limit = ctx->counts.MeshCount; break;
         case IDKPT_ARRAY_MATERIALS: b = &ctx->materials; elem = sizeof(GpuMaterial); limit = ctx->counts.MaterialCount; break;
         case IDKPT_ARRAY_LIGHTS: b = &ctx->lights; elem = sizeof(GpuLight); limit = ctx->counts.LightCount; break;
+        case IDKPT_ARRAY_TLAS_NODES: b = &ctx->tlas; elem = sizeof(GpuTlasNode); limit = ctx->counts.UseTlas ? ctx->counts.TlasNodeCount : 0; break;
         default: return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: unknown array id");
     }
     if (first + count > limit) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: range outside the array");
@@ -557,6 +575,14 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
         for (uint64_t i = 0; i < count; i++)
             if (m[i].MaterialId < 0 || (uint64_t)m[i].MaterialId >= ctx->counts.MaterialCount)
                 return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: GpuMesh.MaterialId out of range");
+    }
+    if (which == IDKPT_ARRAY_TLAS_NODES) {
+        const GpuTlasNode* t = (const GpuTlasNode*)data;
+        for (uint64_t i = 0; i < count; i++) {
+            const uint32_t w = t[i].IsLeafAndChildOrInstanceId, id = w & 0x7FFFFFFFu;
+            if ((w >> 31) ? (id >= ctx->counts.BlasInstanceCount) : (id <= first + i || (uint64_t)id + 1 >= ctx->counts.TlasNodeCount))
+                return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: malformed TLAS node (child / instance id out of range)");
+        }
     }
     if (which == IDKPT_ARRAY_MATERIALS) {
         const GpuMaterial* m = (const GpuMaterial*)data;
@@ -1059,7 +1085,250 @@ IDKPT_API int idkpt_read_wavefront_rays(IdkPtCtx* ctx, GpuWavefrontRay* dst, uin
     return IDKPT_OK;
 }
 
+// ---- present chain ----------------------------------------------------------------------------------------
+
+static inline int ilogb_int(int v) { int r = 0; while (v > 1) { v >>= 1; r++; } return r; }
+
+IDKPT_API int idkpt_post_process(IdkPtCtx* ctx, const IdkPtPostSettings* s, IdkPtImage source, uint8_t* rgba8Out, float* kernelMs) {
+    if (!ctx || !s) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: null argument");
+    if (kernelMs) *kernelMs = 0.0f;
+    const int w = ctx->width, h = ctx->height;
+    const float4* src = nullptr;
+    if (source == IDKPT_IMAGE_GATHERED) {
+        if (ctx->gatherWorld < 2 || ctx->gatherCurrent < 0) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: no gathered frame yet");
+        src = (const float4*)ctx->gatherImage[ctx->gatherCurrent].p;
+    } else if ((int)source >= 0 && (int)source <= 2) {
+        if (ctx->tileCount != 1) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: a tiled context holds only its own rows; use IDKPT_IMAGE_GATHERED");
+        src = (const float4*)ctx->images[source].p;
+    } else return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: unknown image");
+    if (s->IsBloom && (w < 2 || h < 2)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: bloom needs an image of at least 2x2");
+    if (s->IsBloom && (s->BloomMinusLods < 0 || s->BloomMinusLods > 30)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: BloomMinusLods out of range");
+    CK(cudaSetDevice(ctx->device));
+    CK(ensure(ctx->ldr, (size_t)w * h * 4));
+    CK(ensure(ctx->postConsts, sizeof(PostTonemapConsts)));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->stream);
+    const dim3 blk(256);
+    auto grid = [](int gw, int gh) { return dim3((unsigned)((gw + 31) / 32), (unsigned)((gh + 7) / 8)); };
+    PostImage bloomResult = {nullptr, nullptr, 0, 0};
+    if (s->IsBloom) {
+        // Bloom.SetSize (Bloom.cs:132-150): half resolution, levels = max(MaxMipmapLevel - MinusLods, 2); the upsample chain has one level less
+        const int w2 = w / 2, h2 = h / 2;
+        const int levels = std::max(ilogb_int(std::max(w2, h2)) + 1 - s->BloomMinusLods, 2);
+        std::vector<size_t> off(levels + 1, 0);
+        std::vector<int> lw(levels), lh(levels);
+        for (int l = 0; l < levels; l++) {
+            lw[l] = std::max(1, w2 / (1 << std::min(l, 30))); lh[l] = std::max(1, h2 / (1 << std::min(l, 30)));
+            off[l + 1] = off[l] + (size_t)lw[l] * lh[l];
+        }
+        cudaError_t ce = ensure(ctx->bloomDown, off[levels] * 8);
+        if (ce == cudaSuccess) ce = ensure(ctx->bloomUp, off[levels - 1] * 8);
+        if (ce != cudaSuccess) { cudaEventDestroy(e0); cudaEventDestroy(e1); return fail(ctx, IDKPT_ERR_OUT_OF_MEMORY, "idkpt_post_process: bloom allocation failed"); }
+        uint2* down = (uint2*)ctx->bloomDown.p;
+        uint2* up = (uint2*)ctx->bloomUp.p;
+        for (int l = 0; l < levels; l++) {
+            BloomDownArgs a;
+            a.src = l == 0 ? PostImage{src, nullptr, w, h} : PostImage{nullptr, down + off[l - 1], lw[l - 1], lh[l - 1]};
+            a.dst = down + off[l]; a.dw = lw[l]; a.dh = lh[l];
+            a.prefilter = l == 0; a.maxColor = s->BloomMaxColor; a.threshold = s->BloomThreshold;
+            k_bloom_down<<<grid(a.dw, a.dh), blk, 0, ctx->stream>>>(a);
+        }
+        for (int l = levels - 2; l >= 0; l--) {
+            BloomUpArgs a;
+            a.up = l == levels - 2 ? PostImage{nullptr, down + off[l + 1], lw[l + 1], lh[l + 1]} : PostImage{nullptr, up + off[l + 1], lw[l + 1], lh[l + 1]};
+            a.down = PostImage{nullptr, down + off[l + 1], lw[l + 1], lh[l + 1]};
+            a.dst = up + off[l]; a.dw = lw[l]; a.dh = lh[l];
+            k_bloom_up<<<grid(a.dw, a.dh), blk, 0, ctx->stream>>>(a);
+        }
+        bloomResult = PostImage{nullptr, up, lw[0], lh[0]};
+    }
+    k_agx_matrices<<<1, 1, 0, ctx->stream>>>(s->Exposure, s->Compression, (PostTonemapConsts*)ctx->postConsts.p);
+    TonemapArgs t;
+    t.src0 = PostImage{src, nullptr, w, h};
+    t.src1 = bloomResult;
+    t.dst = (uchar4*)ctx->ldr.p; t.w = w; t.h = h;
+    t.saturation = s->Saturation; t.linear = s->Linear; t.peak = s->Peak; t.doTonemap = s->DoTonemapAndSrgbTransform ? 1 : 0;
+    t.consts = (const PostTonemapConsts*)ctx->postConsts.p;
+    k_tonemap<<<grid(w, h), blk, 0, ctx->stream>>>(t);
+    cudaEventRecord(e1, ctx->stream);
+    if (rgba8Out) cudaMemcpyAsync(rgba8Out, ctx->ldr.p, (size_t)w * h * 4, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && kernelMs) cudaEventElapsedTime(kernelMs, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_post_process: ") + cudaGetErrorString(e); return IDKPT_ERR_CUDA; }
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_ldr_device_ptr(IdkPtCtx* ctx, void** devPtr, uint64_t* bytes) {
+    if (!ctx || !devPtr) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_ldr_device_ptr: null argument");
+    if (!ctx->ldr.p) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_ldr_device_ptr: call idkpt_post_process first");
+    *devPtr = ctx->ldr.p;
+    if (bytes) *bytes = (uint64_t)ctx->width * ctx->height * 4;
+    return IDKPT_OK;
+}
+
+// ---- dynamic geometry -----------------------------------------------------------------------------------
+
+IDKPT_API int idkpt_set_skinning_data(IdkPtCtx* ctx, const GpuUnskinnedVertex* vertices, uint64_t count) {
+    if (!ctx || (!vertices && count)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_skinning_data: null argument");
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload(ctx, ctx->unskinned, vertices, count * sizeof(GpuUnskinnedVertex)))) return rc;
+    ctx->unskinnedMaxJoint.resize(count);
+    for (uint64_t i = 0; i < count; i++) {
+        const uint32_t* j = vertices[i].JointIndices;
+        ctx->unskinnedMaxJoint[i] = std::max(std::max(j[0], j[1]), std::max(j[2], j[3]));
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->unskinnedCount = count;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_skin_vertices(IdkPtCtx* ctx, const float* jointMatrices, uint64_t jointCount, const IdkPtSkinningCmd* cmds, uint32_t cmdCount, float* kernelMs) {
+    if (!ctx || (!jointMatrices && jointCount) || (!cmds && cmdCount)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_skin_vertices: null argument");
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_skin_vertices: no scene");
+    if (kernelMs) *kernelMs = 0.0f;
+    const uint64_t vtxLimit = std::min(ctx->counts.VertexPositionCount, ctx->counts.VertexCount);
+    for (uint32_t c = 0; c < cmdCount; c++) {
+        const IdkPtSkinningCmd& k = cmds[c];
+        if ((uint64_t)k.InputVertexOffset + k.VertexCount > ctx->unskinnedCount) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_skin_vertices: input range outside the unskinned vertices (idkpt_set_skinning_data)");
+        if ((uint64_t)k.OutputVertexOffset + k.VertexCount > vtxLimit) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_skin_vertices: output range outside the vertex arrays");
+        uint32_t maxJoint = 0;
+        for (uint64_t i = k.InputVertexOffset; i < (uint64_t)k.InputVertexOffset + k.VertexCount; i++) maxJoint = std::max(maxJoint, ctx->unskinnedMaxJoint[i]);
+        if (k.VertexCount && (uint64_t)k.JointMatricesOffset + maxJoint >= jointCount) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_skin_vertices: a joint index points past the joint matrices");
+    }
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if ((rc = upload(ctx, ctx->joints, jointMatrices, jointCount * 48))) return rc;   // jointMatricesBuffer.UploadElements (ModelManager.cs:277)
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->stream);
+    for (uint32_t c = 0; c < cmdCount; c++) {
+        if (!cmds[c].VertexCount) continue;
+        SkinArgs a;
+        a.unskinned = (const uint32_t*)ctx->unskinned.p; a.joints = (const float4*)ctx->joints.p;
+        a.positions = (float*)ctx->positions.p; a.vertices = (uint4*)ctx->vertices.p; a.vtxFrame = (float4*)ctx->vtxFrame.p;
+        a.inOffset = cmds[c].InputVertexOffset; a.outOffset = cmds[c].OutputVertexOffset; a.jointOffset = cmds[c].JointMatricesOffset; a.count = cmds[c].VertexCount;
+        k_skin_vertices<<<(a.count + 255) / 256, 256, 0, ctx->stream>>>(a);
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && kernelMs) cudaEventElapsedTime(kernelMs, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_skin_vertices: ") + cudaGetErrorString(e); return IDKPT_ERR_CUDA; }
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_blas_refit(IdkPtCtx* ctx, uint32_t first, uint32_t count, float* kernelMs) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_blas_refit: no scene");
+    if ((uint64_t)first + count > ctx->hostDescs.size()) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_blas_refit: BLAS range outside BlasDescs");
+    if (ctx->treeletNodes) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_blas_refit: not available with the treelet node layout (IDKPT_TREELET_PAIRS)");
+    if (kernelMs) *kernelMs = 0.0f;
+    CK(cudaSetDevice(ctx->device));
+    int maxNodes = 0;
+    for (uint32_t b = first; b < first + count; b++) maxNodes = std::max(maxNodes, ctx->hostDescs[b].NodeCount);
+    CK(ensure(ctx->refitParents, std::max<size_t>((size_t)maxNodes, 4) * 4));   // blasRefitLockBuffer sizing, BVH.cs:451
+    CK(ensure(ctx->refitLocks, std::max<size_t>((size_t)maxNodes, 4) * 4));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->stream);
+    for (uint32_t b = first; b < first + count; b++) {
+        const GpuBlasDesc& d = ctx->hostDescs[b];
+        RefitArgs a;
+        a.nodes = (float4*)ctx->nodes.p + 2 * (size_t)d.NodeOffset;
+        a.blasTris = (const int4*)ctx->blasTris.p; a.positions = (const float*)ctx->positions.p;
+        a.triRec = (float4*)((char*)ctx->nodes.p + ctx->nodeBytes);
+        a.parents = (int32_t*)ctx->refitParents.p; a.locks = (uint32_t*)ctx->refitLocks.p;
+        a.nodeCount = (uint32_t)d.NodeCount; a.triOffset = (uint32_t)d.TriangleOffset; a.triCount = (uint32_t)d.TriangleCount;
+        k_refit_prepare<<<(a.nodeCount + 255) / 256, 256, 0, ctx->stream>>>(a);
+        k_refit_climb<<<(a.nodeCount + 255) / 256, 256, 0, ctx->stream>>>(a);
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && kernelMs) cudaEventElapsedTime(kernelMs, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_blas_refit: ") + cudaGetErrorString(e); return IDKPT_ERR_CUDA; }
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_read_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t first, uint64_t count, void* out) {
+    if (!ctx || (!out && count)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_range: null argument");
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_read_range: no scene");
+    const DevBuf* b = nullptr;
+    size_t elem = 0;
+    uint64_t limit = 0;
+    switch (which) {
+        case IDKPT_ARRAY_BLAS_NODES: b = &ctx->nodes; elem = sizeof(GpuBlasNode); limit = ctx->counts.BlasNodeCount; break;
+        case IDKPT_ARRAY_VERTEX_POSITIONS: b = &ctx->positions; elem = sizeof(PackedVec3); limit = ctx->counts.VertexPositionCount; break;
+        case IDKPT_ARRAY_VERTICES: b = &ctx->vertices; elem = sizeof(GpuVertex); limit = ctx->counts.VertexCount; break;
+        case IDKPT_ARRAY_TLAS_NODES: b = &ctx->tlas; elem = sizeof(GpuTlasNode); limit = ctx->counts.UseTlas ? ctx->counts.TlasNodeCount : 0; break;
+        default: return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_range: array id not readable");
+    }
+    if (which == IDKPT_ARRAY_BLAS_NODES && ctx->treeletNodes) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_read_range: BLAS nodes are re-laid out (IDKPT_TREELET_PAIRS)");
+    if (first + count > limit) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_range: range outside the array");
+    CK(cudaSetDevice(ctx->device));
+    if (count) CK(cudaMemcpyAsync(out, (const char*)b->p + first * elem, count * elem, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return IDKPT_OK;
+}
+
+static int trace_rays_impl(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, int32_t traceLights, IdkPtHit* hitsOut, float* kernelMs, bool anyHit);
+
 IDKPT_API int idkpt_trace_rays(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, int32_t traceLights, IdkPtHit* hitsOut, float* kernelMs) {
+    return trace_rays_impl(ctx, rays, count, traceLights, hitsOut, kernelMs, false);
+}
+
+IDKPT_API int idkpt_trace_rays_any(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, int32_t traceLights, IdkPtHit* hitsOut, float* kernelMs) {
+    return trace_rays_impl(ctx, rays, count, traceLights, hitsOut, kernelMs, true);
+}
+
+IDKPT_API int idkpt_shadows_ray_traced(IdkPtCtx* ctx, const GpuPerFrameData* frame, const float* depth, const float* normalRG, int32_t width,
+                                       int32_t height, int32_t lightIndex, int32_t samples, uint32_t noiseIndex, const float* taaJitter,
+                                       float* visibilityOut, float* kernelMs) {
+    if (!ctx || !frame || !depth || !normalRG || !visibilityOut) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_shadows_ray_traced: null argument");
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_shadows_ray_traced: no scene");
+    if (width < 1 || height < 1 || width > 16384 || height > 16384 || samples < 1 || samples > 1024) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_shadows_ray_traced: invalid size / sample count");
+    if (lightIndex < 0 || (uint64_t)lightIndex >= ctx->counts.LightCount) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_shadows_ray_traced: light index out of range");
+    CK(cudaSetDevice(ctx->device));
+    if (kernelMs) *kernelMs = 0.0f;
+    const size_t n = (size_t)width * height;
+    DevBuf dDepth, dN, dVis;
+    int rc = IDKPT_OK;
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
+    do {
+        if (ensure(dDepth, n * 4) != cudaSuccess || ensure(dN, n * 8) != cudaSuccess || ensure(dVis, n * 4) != cudaSuccess) { rc = fail(ctx, IDKPT_ERR_OUT_OF_MEMORY, "idkpt_shadows_ray_traced: device allocation failed"); break; }
+        cudaMemcpyAsync(dDepth.p, depth, n * 4, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(dN.p, normalRG, n * 8, cudaMemcpyHostToDevice, ctx->stream);
+        cudaMemcpyAsync(dVis.p, visibilityOut, n * 4, cudaMemcpyHostToDevice, ctx->stream);   // pixels with depth == 1 keep the caller's value
+        ShadowArgs a;
+        a.sc = ctx->sc;
+        memcpy(a.invProjView, frame->InvProjView, sizeof(a.invProjView));
+        a.jitter[0] = taaJitter ? taaJitter[0] : 0.0f; a.jitter[1] = taaJitter ? taaJitter[1] : 0.0f;
+        a.depth = (const float*)dDepth.p; a.normalRG = (const float2*)dN.p; a.visibility = (float*)dVis.p;
+        a.width = width; a.height = height; a.lightIndex = lightIndex; a.samples = samples; a.noiseIndex = noiseIndex;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        cudaEventRecord(e0, ctx->stream);
+        k_shadows_ray_traced<<<ctx->traceRaysBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(a);
+        cudaEventRecord(e1, ctx->stream);
+        cudaMemcpyAsync(visibilityOut, dVis.p, n * 4, cudaMemcpyDeviceToHost, ctx->stream);
+        cudaError_t e = cudaStreamSynchronize(ctx->stream);
+        if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_shadows_ray_traced: ") + cudaGetErrorString(e); rc = IDKPT_ERR_CUDA; break; }
+        if (kernelMs) cudaEventElapsedTime(kernelMs, e0, e1);
+    } while (0);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    release(dDepth); release(dN); release(dVis);
+    return rc;
+}
+
+static int trace_rays_impl(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, int32_t traceLights, IdkPtHit* hitsOut, float* kernelMs, bool anyHit) {
     if (!ctx || (!rays && count) || (!hitsOut && count)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_trace_rays: null argument");
     if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_trace_rays: no scene");
     if (count >= (1ull << 31)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_trace_rays: too many rays");
@@ -1083,7 +1352,8 @@ IDKPT_API int idkpt_trace_rays(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t cou
         cudaEventCreate(&e0);
         cudaEventCreate(&e1);
         cudaEventRecord(e0, ctx->stream);
-        k_trace_rays<<<ctx->traceRaysBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(a);
+        if (anyHit) k_trace_rays_any<<<ctx->traceRaysBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(a);
+        else k_trace_rays<<<ctx->traceRaysBlocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(a);
         cudaEventRecord(e1, ctx->stream);
         cudaMemcpyAsync(hitsOut, dh.p, count * 32, cudaMemcpyDeviceToHost, ctx->stream);
         cudaError_t e = cudaStreamSynchronize(ctx->stream);

@@ -26,6 +26,8 @@ GpuMaterial = np.dtype([
     ("EmissiveTexture", u8), ("TransmissionTexture", u8), ("IsVolumetric", i4), ("IsDoubleSided", i4)])
 GpuVertex = np.dtype([("TexCoord", f4, 2), ("Tangent", u4), ("Normal", u4)])
 PackedVec3 = np.dtype([("x", f4), ("y", f4), ("z", f4)])
+GpuUnskinnedVertex = np.dtype([("JointIndices", u4, 4), ("JointWeights", f4, 4), ("Position", f4, 3), ("Tangent", u4), ("Normal", u4)])
+IdkPtSkinningCmd = np.dtype([("InputVertexOffset", u4), ("OutputVertexOffset", u4), ("JointMatricesOffset", u4), ("VertexCount", u4)])
 GpuLight = np.dtype([("Position", f4, 3), ("Radius", f4), ("Color", f4, 3), ("PointShadowIndex", i4),
                      ("PrevPosition", f4, 3), ("_pad0", f4)])
 GpuPerFrameData = np.dtype([
@@ -46,7 +48,7 @@ EXPECTED_SIZES = {
     "GpuBlasNode": 32, "GpuBlasTriangle": 16, "GpuBlasDesc": 40, "GpuBlasInstance": 8, "GpuTlasNode": 32,
     "GpuMeshTransform": 144, "GpuMesh": 96, "GpuMaterial": 96, "GpuVertex": 16, "PackedVec3": 12,
     "GpuLight": 48, "GpuPerFrameData": 544, "GpuWavefrontRay": 48, "GpuAovRay": 32, "IdkPtGpuSettings": 20,
-    "IdkPtRay": 32, "IdkPtHit": 32,
+    "IdkPtRay": 32, "IdkPtHit": 32, "GpuUnskinnedVertex": 52, "IdkPtSkinningCmd": 16,
 }
 for _name, _size in EXPECTED_SIZES.items():
     assert globals()[_name].itemsize == _size, (_name, globals()[_name].itemsize, _size)

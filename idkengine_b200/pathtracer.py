@@ -68,6 +68,35 @@ class PathTracer:
         data = np.ascontiguousarray(data)
         self._check(self._lib.idkpt_update_range(self._ctx, which, first, len(data), data.ctypes.data), "idkpt_update_range")
 
+    _READ_DTYPES = {capi.IDKPT_ARRAY_TLAS_NODES: gt.GpuTlasNode, capi.IDKPT_ARRAY_BLAS_NODES: gt.GpuBlasNode,
+                    capi.IDKPT_ARRAY_VERTEX_POSITIONS: gt.PackedVec3, capi.IDKPT_ARRAY_VERTICES: gt.GpuVertex}
+
+    def ReadRange(self, which, first, count):
+        out = np.zeros(count, self._READ_DTYPES[which])
+        self._check(self._lib.idkpt_read_range(self._ctx, which, first, count, out.ctypes.data), "idkpt_read_range")
+        return out
+
+    # ------------------------------------------------------------------ dynamic geometry (ModelManager.Update, ModelManager.cs:236-261)
+    def SetSkinningData(self, unskinned):
+        unskinned = np.ascontiguousarray(unskinned)
+        assert unskinned.dtype == gt.GpuUnskinnedVertex
+        self._check(self._lib.idkpt_set_skinning_data(self._ctx, unskinned.ctypes.data, len(unskinned)), "idkpt_set_skinning_data")
+
+    def SkinVertices(self, joint_matrices, cmds):
+        """joint_matrices: [J, 3, 4] float32 (row-major mat4x3); cmds: IdkPtSkinningCmd array. Returns kernel ms."""
+        jm = np.ascontiguousarray(joint_matrices, np.float32).reshape(-1, 3, 4)
+        cmds = np.ascontiguousarray(cmds)
+        assert cmds.dtype == gt.IdkPtSkinningCmd
+        ms = ctypes.c_float()
+        self._check(self._lib.idkpt_skin_vertices(self._ctx, jm.ctypes.data, len(jm), cmds.ctypes.data, len(cmds), ctypes.byref(ms)), "idkpt_skin_vertices")
+        return ms.value
+
+    def BlasRefit(self, first, count=1):
+        """BVH.GpuBlasesRefit (BVH.cs:472-489). Returns kernel ms."""
+        ms = ctypes.c_float()
+        self._check(self._lib.idkpt_blas_refit(self._ctx, first, count, ctypes.byref(ms)), "idkpt_blas_refit")
+        return ms.value
+
     def SetSky(self, color, faces=None):
         """Constant colour, or cubemap faces [6, N, N, 4] float32 (SkyBoxManager's samplerCube, UBO 5)."""
         s = capi.sky_desc(color, faces)
@@ -180,6 +209,29 @@ class PathTracer:
         self._check(self._lib.idkpt_trace_rays(self._ctx, rays.ctypes.data, len(rays), int(trace_lights),
                                                hits.ctypes.data, ctypes.byref(ms)), "idkpt_trace_rays")
         return hits, ms.value
+
+    def TraceRaysAny(self, rays, trace_lights=False):
+        """Any-hit / occlusion batch (TraceRayAny, BVHIntersect.glsl:299-411). hits["NodePairFetches"] == 1 where occluded."""
+        rays = np.ascontiguousarray(rays)
+        assert rays.dtype == gt.IdkPtRay
+        hits = np.zeros(len(rays), gt.IdkPtHit)
+        ms = ctypes.c_float()
+        self._check(self._lib.idkpt_trace_rays_any(self._ctx, rays.ctypes.data, len(rays), int(trace_lights),
+                                                   hits.ctypes.data, ctypes.byref(ms)), "idkpt_trace_rays_any")
+        return hits, ms.value
+
+    def ShadowsRayTraced(self, frame, depth, normal_rg, light_index, samples=1, noise_index=0, jitter=(0.0, 0.0), visibility=None):
+        """PointShadowManager.ComputeRayTracedShadowMaps for one light: visibility image from a G-buffer (host arrays)."""
+        h, w = depth.shape
+        depth = np.ascontiguousarray(depth, np.float32)
+        nrg = np.ascontiguousarray(normal_rg, np.float32)
+        vis = np.zeros((h, w), np.float32) if visibility is None else np.ascontiguousarray(visibility, np.float32)
+        jit = np.array(jitter, np.float32)
+        frame = np.ascontiguousarray(frame)
+        ms = ctypes.c_float()
+        self._check(self._lib.idkpt_shadows_ray_traced(self._ctx, frame.ctypes.data, depth.ctypes.data, nrg.ctypes.data, w, h, light_index,
+                                                       samples, noise_index, jit.ctypes.data, vis.ctypes.data, ctypes.byref(ms)), "idkpt_shadows_ray_traced")
+        return vis, ms.value
 
     # ---- properties with the reference's reset-on-set behaviour
     def _reset_prop(name, sub=None):  # noqa: N805

@@ -137,6 +137,16 @@ typedef struct GpuVertex {
 } GpuVertex;
 IDK_STATIC_ASSERT(sizeof(GpuVertex) == 16, "GpuVertex must be 16 bytes");
 
+/* SRC/GpuTypes/GpuUnskinnedVertex.cs:5-12, GpuTypes.glsl:283-291 (scalar-packed, 52 bytes). */
+typedef struct GpuUnskinnedVertex {
+    uint32_t JointIndices[4];
+    float    JointWeights[4];
+    float    Position[3];
+    uint32_t Tangent;
+    uint32_t Normal;
+} GpuUnskinnedVertex;
+IDK_STATIC_ASSERT(sizeof(GpuUnskinnedVertex) == 52, "GpuUnskinnedVertex must be 52 bytes");
+
 /* PackedVec3 Positions[] (SSBO 8, StaticStorageBuffers.glsl:44-47): 12 bytes. */
 typedef struct PackedVec3 {
     float x, y, z;

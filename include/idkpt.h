@@ -84,7 +84,11 @@ typedef enum IdkPtArrayId {
     IDKPT_ARRAY_MESH_TRANSFORMS = 0,
     IDKPT_ARRAY_MESHES = 1,
     IDKPT_ARRAY_MATERIALS = 2,
-    IDKPT_ARRAY_LIGHTS = 3
+    IDKPT_ARRAY_LIGHTS = 3,
+    IDKPT_ARRAY_TLAS_NODES = 4,        /* update + read: BVH.TlasBuild re-upload (BVH.cs:278-283); needs a scene set with UseTlas */
+    IDKPT_ARRAY_BLAS_NODES = 5,        /* read only (idkpt_read_range): refitted boxes for the host-side TLAS build */
+    IDKPT_ARRAY_VERTEX_POSITIONS = 6,  /* read only: skinned positions (the download behind fenceCopiedSkinnedVerticesToHost, ModelManager.cs:282) */
+    IDKPT_ARRAY_VERTICES = 7           /* read only: skinned normals / tangents */
 } IdkPtArrayId;
 
 /* Replaces SkyBoxManager's bindless samplerCube in UBO 5 (SkyBoxManager.cs:87):
@@ -205,6 +209,60 @@ IDKPT_API int idkpt_read_wavefront_rays(IdkPtCtx* ctx, GpuWavefrontRay* dst, uin
 
 /* Stand-alone closest-hit batch with host buffers (H2D + kernel + D2H inside). */
 IDKPT_API int idkpt_trace_rays(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, int32_t trace_lights, IdkPtHit* hits_out, float* kernel_ms);
+
+/* ---- "next" rows of the scope table, built on the same traversal code ----
+ * Any-hit (occlusion) batch: TraceRayAny / IntersectBlasAny (BVHIntersect.glsl:107-181,299-411). hits_out[i].NodePairFetches
+ * is 1 if the ray is occluded, 0 otherwise; T/TriangleId/Bary describe the first accepted (not the closest) hit. */
+IDKPT_API int idkpt_trace_rays_any(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, int32_t trace_lights, IdkPtHit* hits_out, float* kernel_ms);
+
+/* Ray-traced point-light shadows: ShadowsRayTraced/compute.glsl for one light (PointShadowManager.ComputeRayTracedShadowMaps,
+ * Source/Render/PointShadowManager.cs:53-75). Host arrays: depth [w*h], octahedral normal rg [w*h*2]; visibility_out [w*h] is
+ * read-modify-write (pixels with depth == 1 are left untouched, as the shader returns early). noise_index = the
+ * (Frame % SampleCount) * samples term (0 without TAA); taa_jitter may be NULL. */
+IDKPT_API int idkpt_shadows_ray_traced(IdkPtCtx* ctx, const GpuPerFrameData* frame, const float* depth, const float* normalRG,
+                                       int32_t width, int32_t height, int32_t light_index, int32_t samples, uint32_t noise_index,
+                                       const float* taa_jitter, float* visibility_out, float* kernel_ms);
+
+/* ---- dynamic geometry: ModelManager.Update = skin -> refit -> TLAS (ModelManager.cs:236-261) ----
+ * idkpt_set_skinning_data: unskinnedVertexSSBO upload (52-byte GpuUnskinnedVertex records).
+ * idkpt_skin_vertices: uploads the joint matrices (row-major mat4x3 = 3 x vec4 each, ModelManager.cs:272-277) and runs
+ *   Skinning/compute.glsl once per command; positions, normals and tangents are rewritten in place on the device.
+ * idkpt_blas_refit: BVH.GpuBlasesRefit(first, count) (BVH.cs:472-489, BLASRefit/compute.glsl); also refreshes the derived
+ *   triangle records of the refitted BLASes. Call it for every BLAS whose vertices moved.
+ * idkpt_read_range: device -> host read-back (refitted BLAS nodes for the host TLAS build, skinned vertices).
+ * All of them reset the accumulation like any other scene edit. */
+typedef struct IdkPtSkinningCmd {     /* ModelManager.SkinningCmd, Skinning/compute.glsl:9-12 uniforms */
+    uint32_t InputVertexOffset;
+    uint32_t OutputVertexOffset;
+    uint32_t JointMatricesOffset;
+    uint32_t VertexCount;
+} IdkPtSkinningCmd;
+
+IDKPT_API int idkpt_set_skinning_data(IdkPtCtx* ctx, const GpuUnskinnedVertex* vertices, uint64_t count);
+IDKPT_API int idkpt_skin_vertices(IdkPtCtx* ctx, const float* joint_matrices, uint64_t joint_count, const IdkPtSkinningCmd* cmds, uint32_t cmd_count, float* kernel_ms);
+IDKPT_API int idkpt_blas_refit(IdkPtCtx* ctx, uint32_t first_blas, uint32_t count, float* kernel_ms);
+IDKPT_API int idkpt_read_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t first, uint64_t count, void* out);
+
+/* ---- present chain: Bloom.Compute(Result) + TonemapAndGamma.Compute(Result, Bloom.Result)
+ * (Application.cs:217-223) -> the RGBA8 frame the reference copies to the swapchain, produced on the device. ---- */
+typedef struct IdkPtPostSettings {
+    float   Exposure;                    /* TonemapAndGammaCorrect.GpuSettings (TonemapAndGammaCorrecter.cs:10-22): 0.45 */
+    float   Saturation;                  /* 1.06 */
+    float   Linear;                      /* 0.18 */
+    float   Peak;                        /* 1.0 */
+    float   Compression;                 /* 0.1 */
+    int32_t DoTonemapAndSrgbTransform;   /* 1 */
+    int32_t IsBloom;                     /* Application.IsBloom, default 1 */
+    float   BloomThreshold;              /* Bloom.GpuSettings (Bloom.cs:10-19): 1.5 */
+    float   BloomMaxColor;               /* 3.8 */
+    int32_t BloomMinusLods;              /* Bloom.MinusLods, default 3 */
+} IdkPtPostSettings;
+
+/* source: IDKPT_IMAGE_RESULT/ALBEDO/NORMAL of an untiled context, or IDKPT_IMAGE_GATHERED (full multi-GPU frame).
+ * rgba8_out: host buffer of width*height*4 bytes (row-major, R8G8B8A8Unorm), or NULL to keep the frame on the device
+ * (idkpt_ldr_device_ptr). */
+IDKPT_API int idkpt_post_process(IdkPtCtx* ctx, const IdkPtPostSettings* settings, IdkPtImage source, uint8_t* rgba8_out, float* kernel_ms);
+IDKPT_API int idkpt_ldr_device_ptr(IdkPtCtx* ctx, void** dev_ptr, uint64_t* bytes);
 
 IDKPT_API uint32_t idkpt_abi_version(void);
 

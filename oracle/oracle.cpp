@@ -1112,3 +1112,294 @@ ORACLE_API uint32_t oracle_pcg(uint32_t seed, uint32_t* nextSeed) { uint32_t s =
 } // extern "C"
 
 #include "oracle_vxgi.inc"
+
+// ------------------------------------------------------------------------------------------------ "next" rows
+// Any-hit traversal (BVHIntersect.glsl:107-181, 299-411) and the ray-traced point-light shadow pass
+// (ShadowsRayTraced/compute.glsl, dispatched by PointShadowManager.ComputeRayTracedShadowMaps, PointShadowManager.cs:53-75).
+namespace {
+
+// IntersectBlasAny, BVHIntersect.glsl:107-181: left-first descent, returns at the first accepted triangle.
+static bool IntersectBlasAny(const Scene& s, const Ray& ray, const GpuBlasDesc& blasDesc, HitInfo& hitInfo, bool useTlas) {
+    float tMinLeft, tMinRight;
+    const GpuBlasNode* nodes = s.d.BlasNodes + blasDesc.NodeOffset;
+    vec3 invDir = {1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z};
+    if (!useTlas) {
+        const GpuBlasNode& rootNode = nodes[1];
+        if (!(RayBoxIntersect(ray, invDir, rootNode.Min, rootNode.Max, tMinLeft) && tMinLeft < hitInfo.T)) return false;
+    }
+    uint32_t stack[256];
+    uint32_t stackPtr = 0, stackTop = 2;
+    while (true) {
+        const GpuBlasNode& leftNode = nodes[stackTop];
+        const GpuBlasNode& rightNode = nodes[stackTop + 1];
+        bool hitLeft = RayBoxIntersect(ray, invDir, leftNode.Min, leftNode.Max, tMinLeft) && tMinLeft <= hitInfo.T;
+        bool hitRight = RayBoxIntersect(ray, invDir, rightNode.Min, rightNode.Max, tMinRight) && tMinRight <= hitInfo.T;
+        bool intersectLeft = hitLeft && leftNode.TriCount > 0;
+        bool intersectRight = hitRight && rightNode.TriCount > 0;
+        if (intersectLeft || intersectRight) {
+            uint32_t first = intersectLeft ? (uint32_t)leftNode.TriStartOrChild : (uint32_t)rightNode.TriStartOrChild;
+            uint32_t end = !intersectRight ? (uint32_t)(leftNode.TriStartOrChild + leftNode.TriCount) : (uint32_t)(rightNode.TriStartOrChild + rightNode.TriCount);
+            first += (uint32_t)blasDesc.TriangleOffset;
+            end += (uint32_t)blasDesc.TriangleOffset;
+            for (uint32_t i = first; i < end; i++) {
+                const GpuBlasTriangle& tri = s.d.BlasTriangles[i];
+                vec3 bary;
+                float hitT;
+                if (RayTriangleIntersect(ray, pos(s, tri.X), pos(s, tri.Y), pos(s, tri.Z), bary, hitT) && hitT < hitInfo.T) {
+                    hitInfo.TriangleId = i;
+                    hitInfo.bx = bary.x;
+                    hitInfo.by = bary.y;
+                    hitInfo.T = hitT;
+                    return true;
+                }
+            }
+        }
+        bool traverseLeft = hitLeft && leftNode.TriCount == 0;
+        bool traverseRight = hitRight && rightNode.TriCount == 0;
+        if (traverseLeft || traverseRight) {
+            if (traverseLeft && traverseRight) {
+                stackTop = leftNode.TriStartOrChild;
+                stack[stackPtr++] = rightNode.TriStartOrChild;
+            } else {
+                stackTop = traverseLeft ? leftNode.TriStartOrChild : rightNode.TriStartOrChild;
+            }
+        } else {
+            if (stackPtr == 0) break;
+            stackTop = stack[--stackPtr];
+        }
+    }
+    return false;
+}
+
+// TraceRayAny, BVHIntersect.glsl:299-411 (no-TLAS instance loop and TLAS walk)
+static bool TraceRayAny(const Scene& s, const Ray& ray, HitInfo& hitInfo, bool traceLights, float maxDist) {
+    hitInfo.T = maxDist;
+    hitInfo.TriangleId = ~0u;
+    hitInfo.MeshTransformId = 0;
+    hitInfo.bx = hitInfo.by = 0.0f;
+    if (traceLights) {
+        float tMin, tMax;
+        for (uint64_t i = 0; i < s.d.LightCount; i++) {
+            const GpuLight& light = s.d.Lights[i];
+            if (RaySphereIntersect(ray, V(light.Position), light.Radius, tMin, tMax) && tMin < hitInfo.T) {
+                hitInfo.T = tMin < 0.0f ? tMax : tMin;
+                hitInfo.MeshTransformId = (uint32_t)i;
+                return true;
+            }
+        }
+    }
+    if (s.d.UseTlas) {
+        float tMinLeft, tMinRight;
+        uint32_t stackPtr = 0, stackTop = 0;
+        uint32_t stack[24];
+        vec3 invDir = {1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z};
+        while (true) {
+            const GpuTlasNode& parent = s.d.TlasNodes[stackTop];
+            bool isLeaf = (parent.IsLeafAndChildOrInstanceId >> 31) == 1;
+            uint32_t id = parent.IsLeafAndChildOrInstanceId & ((1u << 31) - 1);
+            if (isLeaf) {
+                const GpuBlasInstance& inst = s.d.BlasInstances[id];
+                Ray localRay = RayTransform(ray, s.d.MeshTransforms[inst.MeshTransformId].InvModelMatrix);
+                if (IntersectBlasAny(s, localRay, s.d.BlasDescs[inst.BlasId], hitInfo, true)) { hitInfo.MeshTransformId = inst.MeshTransformId; return true; }
+                if (stackPtr == 0) break;
+                stackTop = stack[--stackPtr];
+                continue;
+            }
+            const GpuTlasNode& leftNode = s.d.TlasNodes[id];
+            const GpuTlasNode& rightNode = s.d.TlasNodes[id + 1];
+            bool traverseLeft = RayBoxIntersect(ray, invDir, leftNode.Min, leftNode.Max, tMinLeft) && tMinLeft < hitInfo.T;
+            bool traverseRight = RayBoxIntersect(ray, invDir, rightNode.Min, rightNode.Max, tMinRight) && tMinRight < hitInfo.T;
+            if (traverseLeft || traverseRight) {
+                if (traverseLeft && traverseRight) {
+                    bool leftCloser = tMinLeft < tMinRight;
+                    stackTop = leftCloser ? id : id + 1;
+                    stack[stackPtr++] = leftCloser ? id + 1 : id;
+                } else {
+                    stackTop = traverseLeft ? id : id + 1;
+                }
+            } else {
+                if (stackPtr == 0) break;
+                stackTop = stack[--stackPtr];
+            }
+        }
+    } else {
+        for (uint64_t i = 0; i < s.d.BlasInstanceCount; i++) {
+            const GpuBlasInstance& inst = s.d.BlasInstances[i];
+            Ray localRay = RayTransform(ray, s.d.MeshTransforms[inst.MeshTransformId].InvModelMatrix);
+            if (IntersectBlasAny(s, localRay, s.d.BlasDescs[inst.BlasId], hitInfo, false)) { hitInfo.MeshTransformId = inst.MeshTransformId; return true; }
+        }
+    }
+    return false;
+}
+
+// Math.glsl:104-117 ConstructBasis, Sampling.glsl:21-33 SampleCone, :35-57 SampleSphere(toSphere, radius, ...)
+static vec3 SampleSphereLight(vec3 toSphere, float sphereRadius, float rnd0, float rnd1, float& distanceToSphere) {
+    float radiusSq = sphereRadius * sphereRadius;
+    float distanceSq = dot(toSphere, toSphere);
+    float sinThetaMaxSq = radiusSq / distanceSq;
+    float cosThetaMax = sqrtf(fmaxf(1.0f - sinThetaMaxSq, 0.0f));
+    float phiMax = 2.0f * PI_F;
+    float phi = phiMax * rnd0;
+    float cosTheta = mixf(cosThetaMax, 1.0f, fmaxf(rnd1, 0.001f));
+    float sinTheta = sqrtf(fmaxf(1.0f - cosTheta * cosTheta, 0.0f));
+    distanceToSphere = sqrtf(dot(toSphere, toSphere)) * cosTheta - sqrtf(radiusSq - distanceSq * sinTheta * sinTheta);
+    vec3 normal = normalize(toSphere);
+    float sinPhi, cosPhi;
+    det_sincos(phi, &sinPhi, &cosPhi);
+    vec3 local = {cosPhi * sinTheta, cosTheta, sinPhi * sinTheta};
+    vec3 up = fabsf(normal.z) < 0.999f ? V(0.0f, 0.0f, 1.0f) : V(1.0f, 0.0f, 0.0f);
+    vec3 tangent = normalize(cross(up, normal));
+    vec3 bitangent = cross(normal, tangent);
+    // mat3(tangent, normal, bitangent) * local
+    return (tangent * local.x + normal * local.y) + bitangent * local.z;
+}
+
+} // namespace
+
+extern "C" {
+
+ORACLE_API int oracle_trace_rays_any(const IdkPtSceneDesc* scene, const IdkPtRay* rays, uint64_t count, int traceLights, IdkPtHit* out, int threads) {
+    Scene s; s.d = *scene;
+    parallel_for(count, threads, [&](size_t b, size_t e, int) {
+        for (size_t i = b; i < e; i++) {
+            HitInfo h;
+            bool hit = TraceRayAny(s, Ray{V(rays[i].Origin), V(rays[i].Direction)}, h, traceLights != 0, rays[i].TMax);
+            out[i] = IdkPtHit{h.bx, h.by, h.T, h.TriangleId, h.MeshTransformId, hit ? 1u : 0u, 0, 0};
+        }
+    });
+    return 0;
+}
+
+// ShadowsRayTraced/compute.glsl for one light: visibility image [height][width] (untouched where depth == 1).
+ORACLE_API int oracle_shadows_ray_traced(const IdkPtSceneDesc* scene, const GpuPerFrameData* frame, const float* depth, const float* normalRG,
+                                         int width, int height, int lightIndex, int samples, uint32_t noiseIndex0, const float* taaJitter,
+                                         float* visibilityOut, int threads) {
+    Scene s; s.d = *scene;
+    if (lightIndex < 0 || (uint64_t)lightIndex >= s.d.LightCount || samples < 1) return -1;
+    const GpuLight& light = s.d.Lights[lightIndex];
+    parallel_for((size_t)height, threads, [&](size_t yb, size_t ye, int) {
+        for (size_t y = yb; y < ye; y++)
+            for (int x = 0; x < width; x++) {
+                const size_t p = y * width + x;
+                const float d = depth[p];
+                if (d == 1.0f) continue;
+                const float u = ((float)x + 0.5f) / (float)width, v = ((float)y + 0.5f) / (float)height;
+                const float nx = (u * 2.0f - 1.0f) - taaJitter[0], ny = (v * 2.0f - 1.0f) - taaJitter[1];
+                const float* m = frame->InvProjView;
+                const float wx = ((m[0] * nx + m[4] * ny) + m[8] * d) + m[12] * 1.0f;
+                const float wy = ((m[1] * nx + m[5] * ny) + m[9] * d) + m[13] * 1.0f;
+                const float wz = ((m[2] * nx + m[6] * ny) + m[10] * d) + m[14] * 1.0f;
+                const float ww = ((m[3] * nx + m[7] * ny) + m[11] * d) + m[15] * 1.0f;
+                vec3 fragPos = {wx / ww, wy / ww, wz / ww};
+                vec3 normal = DecodeUnitVec(normalRG[2 * p], normalRG[2 * p + 1]);
+                float cosTheta = dot(normal, normalize(V(light.Position) - fragPos));
+                if (cosTheta <= 0.0f) { visibilityOut[p] = 0.0f; continue; }
+                float visibility = 0.0f;
+                uint32_t noiseIndex = noiseIndex0;
+                for (int i = 0; i < samples; i++) {
+                    vec3 biasedPosition = fragPos + normal * 0.01f;
+                    float rnd0 = InterleavedGradientNoise((float)x, (float)y, noiseIndex + 0);
+                    float rnd1 = InterleavedGradientNoise((float)x, (float)y, noiseIndex + 1);
+                    noiseIndex++;
+                    vec3 fragToLight = V(light.Position) - biasedPosition;
+                    float distanceToLight;
+                    vec3 direction = SampleSphereLight(fragToLight, light.Radius, rnd0, rnd1, distanceToLight);
+                    Ray ray = {biasedPosition, direction};
+                    HitInfo hitInfo;
+                    Counters cnt = {0, 0, 0, 0.0f};
+                    float thisVisibility = 1.0f;
+                    while (TraceRay(s, ray, hitInfo, cnt, true, distanceToLight - 0.001f)) {
+                        if (hitInfo.TriangleId == ~0u) {
+                            if (hitInfo.MeshTransformId != (uint32_t)lightIndex) thisVisibility = 0.0f;
+                            break;
+                        }
+                        const GpuBlasTriangle& tri = s.d.BlasTriangles[hitInfo.TriangleId];
+                        const GpuMesh& mesh = s.d.Meshes[tri.MeshId];
+                        Surface surface = GetSurface(s.d.Materials[mesh.MaterialId]);
+                        SurfaceApplyModificatons(surface, mesh);
+                        if (surface.AlphaCutoff == 2.0f) thisVisibility *= 1.0f - surface.Alpha;
+                        else if (surface.Alpha > surface.AlphaCutoff) thisVisibility = 0.0f;
+                        if (thisVisibility < 0.01f) break;
+                        float dist = hitInfo.T + 0.001f;
+                        ray.o = ray.o + ray.d * dist;
+                        distanceToLight -= dist;
+                    }
+                    visibility += thisVisibility;
+                }
+                visibilityOut[p] = visibility / (float)samples;
+            }
+    });
+    return 0;
+}
+
+} // extern "C"
+
+// ---- dynamic geometry --------------------------------------------------------------------------------------
+// Test infrastructure like the rest of this file: CPU restatement of Skinning/compute.glsl and of BLAS.Refit.
+
+static inline uint32_t CompressSR11G11B10(vec3 v) {
+    // Compression.glsl:1-28; round() half-way case: floor(x + 0.5) (GLSL leaves it to the implementation)
+    const float x = v.x * 0.5f + 0.5f, y = v.y * 0.5f + 0.5f, z = v.z * 0.5f + 0.5f;
+    const uint32_t r = (uint32_t)floorf(x * 2047.0f + 0.5f);
+    const uint32_t g = (uint32_t)floorf(y * 2047.0f + 0.5f);
+    const uint32_t b = (uint32_t)floorf(z * 1023.0f + 0.5f);
+    return (b << 22) | (g << 11) | r;
+}
+
+extern "C" {
+
+// Skinning/compute.glsl:14-49 for one command. joints: row-major mat4x3 (3 x vec4 per joint).
+ORACLE_API void oracle_skin_vertices(const GpuUnskinnedVertex* unskinned, const float* joints, PackedVec3* positions, GpuVertex* vertices,
+                                     uint32_t inOffset, uint32_t outOffset, uint32_t jointOffset, uint32_t count) {
+    for (uint32_t i = 0; i < count; i++) {
+        const GpuUnskinnedVertex& u = unskinned[inOffset + i];
+        float rows[3][4];
+        for (int r = 0; r < 3; r++)
+            for (int c = 0; c < 4; c++) {
+                const float m0 = joints[12 * (size_t)(jointOffset + u.JointIndices[0]) + 4 * r + c];
+                const float m1 = joints[12 * (size_t)(jointOffset + u.JointIndices[1]) + 4 * r + c];
+                const float m2 = joints[12 * (size_t)(jointOffset + u.JointIndices[2]) + 4 * r + c];
+                const float m3 = joints[12 * (size_t)(jointOffset + u.JointIndices[3]) + 4 * r + c];
+                rows[r][c] = ((u.JointWeights[0] * m0 + u.JointWeights[1] * m1) + u.JointWeights[2] * m2) + u.JointWeights[3] * m3;
+            }
+        const vec3 position = {u.Position[0], u.Position[1], u.Position[2]};
+        const vec3 normal = DecompressSR11G11B10(u.Normal), tangent = DecompressSR11G11B10(u.Tangent);
+        float p[3], n[3], t[3];
+        for (int r = 0; r < 3; r++) {
+            p[r] = ((rows[r][0] * position.x + rows[r][1] * position.y) + rows[r][2] * position.z) + rows[r][3] * 1.0f;
+            n[r] = (rows[r][0] * normal.x + rows[r][1] * normal.y) + rows[r][2] * normal.z;
+            t[r] = (rows[r][0] * tangent.x + rows[r][1] * tangent.y) + rows[r][2] * tangent.z;
+        }
+        const vec3 nn = normalize(vec3{n[0], n[1], n[2]}), tt = normalize(vec3{t[0], t[1], t[2]});
+        positions[outOffset + i] = {p[0], p[1], p[2]};
+        vertices[outOffset + i].Normal = CompressSR11G11B10(nn);
+        vertices[outOffset + i].Tangent = CompressSR11G11B10(tt);
+    }
+}
+
+// BLAS.Refit (BLAS.cs:276-293): reverse sweep; the boxes BLASRefit/compute.glsl's leaf-up climb must also produce.
+ORACLE_API void oracle_blas_refit(GpuBlasNode* allNodes, const GpuBlasDesc* desc, const GpuBlasTriangle* blasTriangles, const PackedVec3* positions) {
+    GpuBlasNode* nodes = allNodes + desc->NodeOffset;
+    for (int i = desc->NodeCount - 1; i >= 1; i--) {
+        GpuBlasNode& nd = nodes[i];
+        if (nd.TriCount > 0) {
+            float lo[3] = {3.4028235e38f, 3.4028235e38f, 3.4028235e38f}, hi[3] = {-3.4028235e38f, -3.4028235e38f, -3.4028235e38f};
+            for (int k = 0; k < nd.TriCount; k++) {
+                const GpuBlasTriangle& t = blasTriangles[desc->TriangleOffset + nd.TriStartOrChild + k];
+                const int idx[3] = {t.X, t.Y, t.Z};
+                for (int v = 0; v < 3; v++) {
+                    const PackedVec3& p = positions[idx[v]];
+                    lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+                    hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+                }
+            }
+            for (int c = 0; c < 3; c++) { nd.Min[c] = lo[c]; nd.Max[c] = hi[c]; }
+            continue;
+        }
+        const GpuBlasNode& l = nodes[nd.TriStartOrChild];
+        const GpuBlasNode& r = nodes[nd.TriStartOrChild + 1];
+        for (int c = 0; c < 3; c++) { nd.Min[c] = fminf(l.Min[c], r.Min[c]); nd.Max[c] = fmaxf(l.Max[c], r.Max[c]); }
+    }
+}
+
+} // extern "C"

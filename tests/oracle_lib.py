@@ -70,6 +70,51 @@ def trace_rays(scene, rays, trace_lights=False, threads=None):
     return out
 
 
+def trace_rays_any(scene, rays, trace_lights=False, threads=None):
+    d, keep = capi.scene_desc(scene)
+    out = np.zeros(len(rays), gt.IdkPtHit)
+    L = lib()
+    L.oracle_trace_rays_any.argtypes = [ctypes.POINTER(capi.IdkPtSceneDesc), ctypes.c_void_p, ctypes.c_uint64, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int32]
+    L.oracle_trace_rays_any(ctypes.byref(d), rays.ctypes.data, len(rays), int(trace_lights), out.ctypes.data, threads or default_threads())
+    return out
+
+
+def shadows_ray_traced(scene, frame, depth, normal_rg, light_index, samples=1, noise_index=0, jitter=(0.0, 0.0), visibility=None, threads=None):
+    d, keep = capi.scene_desc(scene)
+    h, w = depth.shape
+    depth = np.ascontiguousarray(depth, np.float32)
+    nrg = np.ascontiguousarray(normal_rg, np.float32)
+    vis = np.zeros((h, w), np.float32) if visibility is None else np.ascontiguousarray(visibility, np.float32)
+    jit = np.array(jitter, np.float32)
+    L = lib()
+    L.oracle_shadows_ray_traced.restype = ctypes.c_int32
+    L.oracle_shadows_ray_traced.argtypes = [ctypes.POINTER(capi.IdkPtSceneDesc), ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32,
+                                            ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32]
+    rc = L.oracle_shadows_ray_traced(ctypes.byref(d), frame.ctypes.data, depth.ctypes.data, nrg.ctypes.data, w, h, light_index, samples, noise_index,
+                                     jit.ctypes.data, vis.ctypes.data, threads or default_threads())
+    assert rc == 0
+    return vis
+
+
+def skin_vertices(unskinned, joint_matrices, positions, vertices, cmd):
+    """In-place oracle_skin_vertices on numpy arrays (positions: PackedVec3, vertices: GpuVertex)."""
+    L = lib()
+    L.oracle_skin_vertices.restype = None
+    L.oracle_skin_vertices.argtypes = [ctypes.c_void_p] * 4 + [ctypes.c_uint32] * 4
+    jm = np.ascontiguousarray(joint_matrices, np.float32)
+    L.oracle_skin_vertices(unskinned.ctypes.data, jm.ctypes.data, positions.ctypes.data, vertices.ctypes.data, int(cmd["InputVertexOffset"]),
+                           int(cmd["OutputVertexOffset"]), int(cmd["JointMatricesOffset"]), int(cmd["VertexCount"]))
+
+
+def blas_refit(scene, blas_id):
+    """In-place BLAS.Refit of scene.blas_nodes for one BLAS from scene.positions."""
+    L = lib()
+    L.oracle_blas_refit.restype = None
+    L.oracle_blas_refit.argtypes = [ctypes.c_void_p] * 4
+    desc = np.ascontiguousarray(scene.blas_descs[blas_id:blas_id + 1])
+    L.oracle_blas_refit(scene.blas_nodes.ctypes.data, desc.ctypes.data, scene.blas_triangles.ctypes.data, scene.positions.ctypes.data)
+
+
 def brute_force(scene, rays, threads=None):
     d, keep = capi.scene_desc(scene)
     out = np.zeros(len(rays), gt.IdkPtHit)

@@ -387,3 +387,64 @@ def test_multi_gpu_peer_gather():
     out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                           "--master-port", "29541", os.path.join(repo, "scripts", "check_peer_gather.py")], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0 and "PEER_GATHER_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
+
+
+# ---- scope table 8f.1: any-hit traversal and ray-traced shadows ---------------------------------------------------
+
+@pytest.mark.parametrize("name", ["cornell", "multi_blas", "atrium_small"])
+def test_trace_rays_any_bit_exact(name, request):
+    scene, cam = request.getfixturevalue(name)
+    frame = scenes.camera_frame(cam, 160, 90)
+    rays = np.concatenate([ol.gui_test_rays(frame, 160, 90), random_rays(20000, -2.5, 2.5, 13)])
+    rays["TMax"][::4] = 2.0
+    for lights in (False, True):
+        with PathTracer(64, 64) as pt:
+            pt.SetScene(scene)
+            g, _ = pt.TraceRaysAny(rays, trace_lights=lights)
+            closest, _ = pt.TraceRays(rays, trace_lights=lights)
+        o = ol.trace_rays_any(scene, rays, trace_lights=lights)
+        for f in ("T", "TriangleId", "MeshTransformId", "NodePairFetches"):
+            assert np.array_equal(g[f], o[f]), f
+        for f in ("BaryX", "BaryY"):
+            assert np.array_equal(g[f].view(np.uint32), o[f].view(np.uint32)), f
+        # occluded exactly when the closest-hit query finds something in range
+        assert np.array_equal(g["NodePairFetches"] == 1, closest["T"] != rays["TMax"])
+        assert 0.2 < (g["NodePairFetches"] == 1).mean() < 1.0
+
+
+def test_trace_rays_any_tlas():
+    scene, cam = scenes.multi_blas(threads=1)
+    scene.build_tlas()
+    rays = random_rays(20000, -2.5, 2.5, 17)
+    with PathTracer(64, 64) as pt:
+        pt.SetScene(scene)
+        g, _ = pt.TraceRaysAny(rays)
+    o = ol.trace_rays_any(scene, rays)
+    for f in ("T", "TriangleId", "MeshTransformId", "NodePairFetches"):
+        assert np.array_equal(g[f], o[f]), f
+
+
+@pytest.mark.parametrize("name,samples", [("cornell", 1), ("multi_blas", 4)])
+def test_shadows_ray_traced_bit_exact(name, samples):
+    scene, cam = scenes.cornell_1k(threads=1) if name == "cornell" else scenes.multi_blas(threads=1)
+    if len(scene.lights) == 0:
+        scene.add_light((0.0, 1.6, 0.0), (20.0, 20.0, 20.0), 0.15)
+    w, h = 192, 128
+    frame = scenes.camera_frame(cam, w, h)
+    depth, nrg, _ = ol.synth_gbuffer(scene, frame, w, h)
+    with PathTracer(64, 64) as pt:
+        pt.SetScene(scene)
+        g, ms = pt.ShadowsRayTraced(frame, depth, nrg, 0, samples=samples, noise_index=3 * samples)
+    o = ol.shadows_ray_traced(scene, frame, depth, nrg, 0, samples=samples, noise_index=3 * samples)
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+    lit = g[depth < 1.0]
+    assert (lit == 0.0).any() and (lit == 1.0).any()      # both shadowed and lit pixels exist
+
+
+def test_shadows_errors(cornell):
+    scene, cam = cornell
+    frame = scenes.camera_frame(cam, 32, 32)
+    with PathTracer(32, 32) as pt:
+        pt.SetScene(scene)
+        with pytest.raises(RuntimeError):
+            pt.ShadowsRayTraced(frame, np.ones((32, 32), np.float32), np.zeros((32, 32, 2), np.float32), 99)

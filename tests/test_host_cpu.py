@@ -11,6 +11,7 @@ import pytest
 
 import oracle_lib as ol
 from idkengine_b200 import build, capi, scenes, multigpu
+from idkengine_b200 import gpu_types as gt
 
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
@@ -163,3 +164,28 @@ def test_two_rank_gloo_tile_gather(tmp_path):
                          capture_output=True, text=True, env=env, timeout=300)
     assert out.returncode == 0, out.stderr[-2000:]
     assert "GLOO_OK" in out.stdout
+
+
+def test_oracle_any_hit_and_shadows(multi_blas):
+    """Oracle-only sanity for the 8f.1 rows: any-hit occlusion == closest-hit "found something"; the shadow pass is dark
+    behind occluders, lit in the open, and leaves sky pixels untouched."""
+    scene, cam = multi_blas
+    rng = np.random.default_rng(4)
+    rays = np.zeros(6000, gt.IdkPtRay)
+    rays["Origin"] = rng.uniform(-2.5, 2.5, (6000, 3)).astype(np.float32)
+    d = rng.normal(size=(6000, 3))
+    rays["Direction"] = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
+    rays["TMax"] = np.float32(3.4028235e38)
+    rays["TMax"][::3] = 1.0
+    a = ol.trace_rays_any(scene, rays, trace_lights=True)
+    c = ol.trace_rays(scene, rays, trace_lights=True)
+    assert np.array_equal(a["NodePairFetches"] == 1, c["T"] != rays["TMax"])
+    assert (a["T"][a["NodePairFetches"] == 1] >= c["T"][a["NodePairFetches"] == 1]).all()   # first accepted hit is never closer than the closest
+    w, h = 96, 64
+    frame = scenes.camera_frame(cam, w, h)
+    depth, nrg, _ = ol.synth_gbuffer(scene, frame, w, h)
+    vis0 = np.full((h, w), 7.0, np.float32)
+    vis = ol.shadows_ray_traced(scene, frame, depth, nrg, 0, samples=2, visibility=vis0.copy())
+    assert (vis[depth == 1.0] == 7.0).all()
+    inside = vis[depth < 1.0]
+    assert ((inside >= 0.0) & (inside <= 1.0)).all() and (inside == 0.0).any() and (inside == 1.0).any()
