@@ -80,8 +80,19 @@ EXPORTS = [
     "idkpt_gather_export", "idkpt_gather_import", "idkpt_gather_device_ptr",
     "idkpt_result_device_ptr", "idkpt_tile_rows",
     "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_trace_rays_any", "idkpt_shadows_ray_traced",
-    "idkpt_set_skinning_data", "idkpt_skin_vertices", "idkpt_blas_refit", "idkpt_read_range", "idkpt_abi_version",
+    "idkpt_set_skinning_data", "idkpt_skin_vertices", "idkpt_blas_refit", "idkpt_read_range", "idkpt_post_process", "idkpt_ldr_device_ptr", "idkpt_abi_version",
 ]
+
+
+class IdkPtPostSettings(ctypes.Structure):
+    _fields_ = [("Exposure", c_f), ("Saturation", c_f), ("Linear", c_f), ("Peak", c_f), ("Compression", c_f),
+                ("DoTonemapAndSrgbTransform", c_i32), ("IsBloom", c_i32), ("BloomThreshold", c_f), ("BloomMaxColor", c_f),
+                ("BloomMinusLods", c_i32)]
+
+
+def default_post_settings():
+    """TonemapAndGammaCorrect.GpuSettings + Bloom.GpuSettings defaults (TonemapAndGammaCorrecter.cs:10-22, Bloom.cs:10-19,46)."""
+    return IdkPtPostSettings(0.45, 1.06, 0.18, 1.0, 0.1, 1, 1, 1.5, 3.8, 3)
 
 
 def default_settings():
@@ -213,6 +224,10 @@ def load(path=None):
     L.idkpt_blas_refit.argtypes = [c_vp, c_u32, c_u32, P(c_f)]
     L.idkpt_read_range.restype = c_i32
     L.idkpt_read_range.argtypes = [c_vp, c_i32, c_u64, c_u64, c_vp]
+    L.idkpt_post_process.restype = c_i32
+    L.idkpt_post_process.argtypes = [c_vp, P(IdkPtPostSettings), c_i32, c_vp, P(c_f)]
+    L.idkpt_ldr_device_ptr.restype = c_i32
+    L.idkpt_ldr_device_ptr.argtypes = [c_vp, P(c_vp), P(c_u64)]
     L.idkpt_abi_version.restype = c_u32
     L.idkpt_abi_version.argtypes = []
     if path == _build.LIBIDKPT:

@@ -76,6 +76,16 @@ class PathTracer:
         self._check(self._lib.idkpt_read_range(self._ctx, which, first, count, out.ctypes.data), "idkpt_read_range")
         return out
 
+    # ------------------------------------------------------------------ present chain (Application.cs:217-223)
+    def PostProcess(self, settings=None, source=capi.IDKPT_IMAGE_RESULT, download=True):
+        """Bloom + TonemapAndGammaCorrect of the accumulated frame. Returns (rgba8 [H, W, 4] or None, kernel ms)."""
+        st = settings if settings is not None else capi.default_post_settings()
+        out = np.zeros((self.height, self.width, 4), np.uint8) if download else None
+        ms = ctypes.c_float()
+        self._check(self._lib.idkpt_post_process(self._ctx, ctypes.byref(st), source, out.ctypes.data if download else None, ctypes.byref(ms)),
+                    "idkpt_post_process")
+        return out, ms.value
+
     # ------------------------------------------------------------------ dynamic geometry (ModelManager.Update, ModelManager.cs:236-261)
     def SetSkinningData(self, unskinned):
         unskinned = np.ascontiguousarray(unskinned)

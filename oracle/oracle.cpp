@@ -1403,3 +1403,4 @@ ORACLE_API void oracle_blas_refit(GpuBlasNode* allNodes, const GpuBlasDesc* desc
 }
 
 } // extern "C"
+#include "oracle_post.inc"

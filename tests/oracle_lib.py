@@ -115,6 +115,23 @@ def blas_refit(scene, blas_id):
     L.oracle_blas_refit(scene.blas_nodes.ctypes.data, desc.ctypes.data, scene.blas_triangles.ctypes.data, scene.positions.ctypes.data)
 
 
+def post_process(result, settings=None, want_bloom=False, threads=None):
+    """oracle_post_process on an rgba32f image [H, W, 4] -> rgba8 [H, W, 4] (and Bloom.Result [H//2, W//2, 3])."""
+    st = settings if settings is not None else capi.default_post_settings()
+    h, w = result.shape[:2]
+    result = np.ascontiguousarray(result, np.float32)
+    out = np.zeros((h, w, 4), np.uint8)
+    bloom = np.zeros((max(h // 2, 1), max(w // 2, 1), 3), np.float32)
+    L = lib()
+    L.oracle_post_process.restype = ctypes.c_int32
+    L.oracle_post_process.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(capi.IdkPtPostSettings), ctypes.c_void_p,
+                                      ctypes.c_void_p, ctypes.c_int32]
+    rc = L.oracle_post_process(result.ctypes.data, w, h, ctypes.byref(st), out.ctypes.data, bloom.ctypes.data if want_bloom else None,
+                               threads or default_threads())
+    assert rc == 0
+    return (out, bloom) if want_bloom else out
+
+
 def brute_force(scene, rays, threads=None):
     d, keep = capi.scene_desc(scene)
     out = np.zeros(len(rays), gt.IdkPtHit)
