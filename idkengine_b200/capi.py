@@ -23,6 +23,14 @@ class IdkPtCreateInfo(ctypes.Structure):
                 ("TileIndex", c_i32), ("TileCount", c_i32), ("Flags", c_u32)]
 
 
+IDKPT_TEX_RGBA8_UNORM, IDKPT_TEX_RGBA8_SRGB = 0, 1
+GL_REPEAT, GL_CLAMP_TO_EDGE, GL_MIRRORED_REPEAT = 10497, 33071, 33648
+
+
+class IdkPtTextureDesc(ctypes.Structure):
+    _fields_ = [("Pixels", c_vp), ("Width", c_i32), ("Height", c_i32), ("Format", c_i32), ("WrapS", c_i32), ("WrapT", c_i32), ("_pad0", c_i32)]
+
+
 class IdkPtSceneDesc(ctypes.Structure):
     _fields_ = [
         ("BlasNodes", c_vp), ("BlasNodeCount", c_u64),
@@ -37,6 +45,7 @@ class IdkPtSceneDesc(ctypes.Structure):
         ("VertexPositions", c_vp), ("VertexPositionCount", c_u64),
         ("Lights", c_vp), ("LightCount", c_u64),
         ("UseTlas", c_i32), ("BlasStackSize", c_i32),
+        ("Textures", c_vp), ("TextureCount", c_u64),
     ]
 
 
@@ -134,6 +143,16 @@ def scene_desc(scene):
     d.Lights, d.LightCount = ptr(scene.lights), len(scene.lights)
     d.UseTlas = int(scene.use_tlas)
     d.BlasStackSize = int(scene.blas_stack_size)
+    textures = getattr(scene, "textures", [])
+    if textures:
+        arr = (IdkPtTextureDesc * len(textures))()
+        for i, t in enumerate(textures):
+            px = np.ascontiguousarray(t["pixels"], np.uint8)
+            keep.append(px)
+            arr[i] = IdkPtTextureDesc(px.ctypes.data, px.shape[1], px.shape[0], IDKPT_TEX_RGBA8_SRGB if t.get("srgb") else IDKPT_TEX_RGBA8_UNORM,
+                                      t.get("wrap_s", GL_REPEAT), t.get("wrap_t", GL_REPEAT), 0)
+        keep.append(arr)
+        d.Textures, d.TextureCount = ctypes.addressof(arr), len(textures)
     return d, keep
 
 

@@ -39,6 +39,18 @@ struct DeviceScene {
     int treeletNodes;             // node indices < treeletNodes (BFS-first re-layout, single-BLAS scenes) are staged in shared memory
     const float4* vtxFrame;       // device-private, 2 x float4 per vertex: decoded (normal.xyz, tangent.x) (tangent.yz, 0, 0)
     const float4* surfRec;        // device-private, 5 x float4 per mesh: GetSurface + SurfaceApplyModificatons, see k_prepare_surfaces
+    const struct TexRec* textures; // material texture table (handle k > 0 = textures[k - 1]; 0 = the reference's 1x1 white fallback)
+    uint32_t textureCount;
+    const float* srgbLut;         // 256-entry sRGB -> linear decode table
+};
+
+// One 2-D RGBA8 texture, base level only: compute shaders sample lod 0 (Surface.glsl:57-60).
+struct TexRec {
+    const uchar4* px;
+    int w, h;
+    int wrapS, wrapT;             // GL enums: 10497 REPEAT, 33071 CLAMP_TO_EDGE, 33648 MIRRORED_REPEAT
+    int srgb;                     // rgb decoded through srgbLut before filtering (GL_SRGB8_ALPHA8)
+    int pad;
 };
 
 #define IDK_TLAS_STACK_SIZE 24   // BVHIntersect.glsl:4
@@ -96,7 +108,8 @@ __global__ void k_prepare_vertices(const uint4* __restrict__ vertices, float4* _
 // Scene upload / mesh-material edits: with constant (1x1 white) textures the Surface of a hit depends only on its mesh:
 // GetSurface(material) (Surface.glsl:49-77) followed by SurfaceApplyModificatons(mesh) (Surface.glsl:85-96).
 //   [0] Albedo.xyz, Alpha   [1] Emissive.xyz, Metallic   [2] Absorbance.xyz, Roughness
-//   [3] Transmission, IOR, AlphaCutoff, NormalMapStrength   [4] flags (bit0 IsVolumetric, bit1 TintOnTransmissive)
+//   [3] Transmission, IOR, AlphaCutoff, NormalMapStrength   [4] flags (bit0 IsVolumetric, bit1 TintOnTransmissive,
+//   bit2 material has textures: the record is then only valid for the flags; surface_textured() evaluates the hit)
 __global__ void k_prepare_surfaces(const GpuMesh* __restrict__ meshes, const GpuMaterial* __restrict__ materials,
                                    float4* __restrict__ surfRec, uint32_t meshCount) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -114,7 +127,8 @@ __global__ void k_prepare_surfaces(const GpuMesh* __restrict__ meshes, const Gpu
     const float roughness = clamp1(mat.RoughnessFactor + mesh.RoughnessBias, 0.0f, 1.0f);
     const float transmission = clamp1(mat.TransmissionFactor + mesh.TransmissionBias, 0.0f, 1.0f);
     const float ior = fmaxf(mat.IOR + mesh.IORBias, 1.0f);
-    const uint32_t flags = (mat.IsVolumetric != 0 ? 1u : 0u) | (mesh.TintOnTransmissive != 0 ? 2u : 0u);
+    const bool textured = (mat.BaseColorTexture | mat.MetallicRoughnessTexture | mat.NormalTexture | mat.EmissiveTexture | mat.TransmissionTexture) != 0;
+    const uint32_t flags = (mat.IsVolumetric != 0 ? 1u : 0u) | (mesh.TintOnTransmissive != 0 ? 2u : 0u) | (textured ? 4u : 0u);
     float4* o = surfRec + 5 * (size_t)i;
     o[0] = make_float4(albedo.x, albedo.y, albedo.z, alpha);
     o[1] = make_float4(emissive.x, emissive.y, emissive.z, metallic);
@@ -670,6 +684,75 @@ struct Surface {
     bool IsVolumetric, TintOnTransmissive;
 };
 
+
+// ---- material textures: texture(sampler2D, uv) at lod 0 = bilinear on the base level, evaluated explicitly in fp32
+// (same rule as the sky faces / VXGI grid), wrap modes of the glTF sampler (ModelLoader.cs:1166-1196).
+__device__ __forceinline__ int tex_wrap(int i, int n, int mode) {
+    if (mode == 33071) return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+    if (mode == 33648) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
+    int m = i % n;
+    return m < 0 ? m + n : m;
+}
+__device__ __forceinline__ float4 tex_fetch(const TexRec& t, const float* lut, int x, int y) {
+    const uchar4 c = __ldg(t.px + (size_t)y * t.w + x);
+    if (t.srgb) return make_float4(__ldg(lut + c.x), __ldg(lut + c.y), __ldg(lut + c.z), (float)c.w / 255.0f);
+    return make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+}
+__device__ __forceinline__ float4 tex_lerp(float4 a, float4 b, float t) {
+    const float s = 1.0f - t;
+    return make_float4(a.x * s + b.x * t, a.y * s + b.y * t, a.z * s + b.z * t, a.w * s + b.w * t);
+}
+__device__ __forceinline__ float4 tex_sample(const DeviceScene& sc, unsigned long long handle, float u, float v) {
+    if (handle == 0) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    const TexRec& t = sc.textures[handle - 1];
+    if (t.wrapS == 10497) u = u - floorf(u);
+    if (t.wrapT == 10497) v = v - floorf(v);
+    const float px = u * (float)t.w - 0.5f, py = v * (float)t.h - 0.5f;
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float fx = px - fx0, fy = py - fy0;
+    const int x0 = tex_wrap((int)fx0, t.w, t.wrapS), x1 = tex_wrap((int)fx0 + 1, t.w, t.wrapS);
+    const int y0 = tex_wrap((int)fy0, t.h, t.wrapT), y1 = tex_wrap((int)fy0 + 1, t.h, t.wrapT);
+    const float4 a = tex_lerp(tex_fetch(t, sc.srgbLut, x0, y0), tex_fetch(t, sc.srgbLut, x1, y0), fx);
+    const float4 b = tex_lerp(tex_fetch(t, sc.srgbLut, x0, y1), tex_fetch(t, sc.srgbLut, x1, y1), fx);
+    return tex_lerp(a, b, fy);
+}
+// Interpolate(vec2, vec2, vec2, bary) of the hit triangle's TexCoords (Math.glsl:54-57)
+__device__ __forceinline__ void interp_texcoord(const DeviceScene& sc, int4 tri, float b0, float b1, float b2, float& u, float& v) {
+    const uint4 v0 = __ldg(sc.vertices + tri.x), v1 = __ldg(sc.vertices + tri.y), v2 = __ldg(sc.vertices + tri.z);
+    u = (__uint_as_float(v0.x) * b0 + __uint_as_float(v1.x) * b1) + __uint_as_float(v2.x) * b2;
+    v = (__uint_as_float(v0.y) * b0 + __uint_as_float(v1.y) * b1) + __uint_as_float(v2.y) * b2;
+}
+// GetSurface(material, uv) + SurfaceApplyModificatons(mesh) (Surface.glsl:49-96) with real textures.
+__device__ __forceinline__ void surface_textured(const DeviceScene& sc, int meshId, float u, float v, Surface& s) {
+    const GpuMesh& mesh = sc.meshes[meshId];
+    const GpuMaterial& m = sc.materials[mesh.MaterialId];
+    const uint32_t c = m.BaseColorFactor;
+    const float4 base = tex_sample(sc, m.BaseColorTexture, u, v);
+    s.Albedo = mk3(base.x * ((float)(c & 255u) / 255.0f), base.y * ((float)((c >> 8) & 255u) / 255.0f), base.z * ((float)((c >> 16) & 255u) / 255.0f));
+    s.Alpha = base.w * ((float)((c >> 24) & 255u) / 255.0f);
+    const float4 nt = tex_sample(sc, m.NormalTexture, u, v);
+    s.Normal = mk3(nt.x * 2.0f - 1.0f, nt.y * 2.0f - 1.0f, sqrtf(fmaxf(1.0f - (nt.x * nt.x + nt.y * nt.y), 0.0f)));   // ReconstructPackedNormal
+    const float4 et = tex_sample(sc, m.EmissiveTexture, u, v);
+    s.Emissive = mk3(et.x * m.EmissiveFactor[0], et.y * m.EmissiveFactor[1], et.z * m.EmissiveFactor[2]);
+    s.Absorbance = mk3(m.Absorbance[0], m.Absorbance[1], m.Absorbance[2]);
+    const float4 mr = tex_sample(sc, m.MetallicRoughnessTexture, u, v);
+    s.Metallic = mr.x * m.MetallicFactor;
+    s.Roughness = mr.y * m.RoughnessFactor;
+    s.Transmission = tex_sample(sc, m.TransmissionTexture, u, v).x * m.TransmissionFactor;
+    s.IOR = m.IOR;
+    s.AlphaCutoff = m.AlphaCutoff;
+    s.IsVolumetric = m.IsVolumetric != 0;
+    // SurfaceApplyModificatons
+    s.Emissive = s.Emissive * 1.0f + mesh.EmissiveBias * s.Albedo;
+    const f3 ab = s.Absorbance + mk3(mesh.AbsorbanceBias[0], mesh.AbsorbanceBias[1], mesh.AbsorbanceBias[2]);
+    s.Absorbance = mk3(fmaxf(ab.x, 0.0f), fmaxf(ab.y, 0.0f), fmaxf(ab.z, 0.0f));
+    s.Metallic = clamp1(s.Metallic + mesh.SpecularBias, 0.0f, 1.0f);
+    s.Roughness = clamp1(s.Roughness + mesh.RoughnessBias, 0.0f, 1.0f);
+    s.Transmission = clamp1(s.Transmission + mesh.TransmissionBias, 0.0f, 1.0f);
+    s.IOR = fmaxf(s.IOR + mesh.IORBias, 1.0f);
+    s.TintOnTransmissive = mesh.TintOnTransmissive != 0;
+}
+
 // texture(skyBoxUBO.Albedo, dir).rgb: GL cube-map face selection (spec table 8.19), bilinear inside the face, clamp to edge.
 __device__ __forceinline__ f3 sample_sky(const DeviceScene& sc, f3 d) {
     if (sc.skyFaceSize == 0) return mk3(sc.skyR, sc.skyG, sc.skyB);
@@ -722,6 +805,8 @@ __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, uint32
 
 // One thread per alive ray, no block-level cooperation: every warp runs at its own pace (the ordered compaction of
 // the reference's atomic alive list is a separate, uniform-cost pass over 4-byte entries: k_compact).
+// TEX = the scene has material textures (idkpt_set_scene); the untextured instantiation is the north-star path.
+template <bool TEX>
 __global__ void __launch_bounds__(IDK_BLOCK, 3) k_shade(ShadeArgs a) {
     const uint32_t count = *a.count;
     const DeviceScene& sc = a.sc;
@@ -800,6 +885,11 @@ __global__ void __launch_bounds__(IDK_BLOCK, 3) k_shade(ShadeArgs a) {
                     s.AlphaCutoff = s3.z;
                     s.IsVolumetric = (__float_as_uint(s4.x) & 1u) != 0;
                     s.TintOnTransmissive = (__float_as_uint(s4.x) & 2u) != 0;
+                    if (TEX && (__float_as_uint(s4.x) & 4u)) {
+                        float tu, tv;
+                        interp_texcoord(sc, tri, b0, b1, b2, tu, tv);
+                        surface_textured(sc, tri.w, tu, tv, s);
+                    }
 
                     const float alphaCutoff = (s.AlphaCutoff == 2.0f) ? rnd01(rng) : s.AlphaCutoff;
                     if (s.Alpha < alphaCutoff) {

@@ -222,7 +222,14 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_shadows_ray_traced(ShadowArgs a) 
                 }
                 const int4 tri = __ldg(sc.blasTris + hit.tri);
                 const float4* sr = sc.surfRec + 5 * (size_t)tri.w;
-                const float alpha = ldg4(sr).w, alphaCutoff = ldg4(sr + 3).z;
+                float alpha = ldg4(sr).w;
+                const float alphaCutoff = ldg4(sr + 3).z;
+                if (__float_as_uint(ldg4(sr + 4).x) & 4u) {   // textured material: alpha = texture(BaseColor, uv).a * factor.a
+                    float tu, tv;
+                    interp_texcoord(sc, tri, hit.bx, hit.by, 1.0f - hit.bx - hit.by, tu, tv);
+                    const GpuMaterial& m = sc.materials[sc.meshes[tri.w].MaterialId];
+                    alpha = tex_sample(sc, m.BaseColorTexture, tu, tv).w * ((float)((m.BaseColorFactor >> 24) & 255u) / 255.0f);
+                }
                 if (alphaCutoff == 2.0f) thisVisibility *= 1.0f - alpha;
                 else if (alpha > alphaCutoff) thisVisibility = 0.0f;
                 if (thisVisibility < 0.01f) break;

@@ -17,7 +17,7 @@
 #include "idk_dynamic.cuh"
 #include "idk_post.cuh"
 
-#define IDKPT_ABI_VERSION 1u
+#define IDKPT_ABI_VERSION 2u   // 2: IdkPtSceneDesc gained Textures / TextureCount
 
 static thread_local std::string g_createError;
 
@@ -47,6 +47,7 @@ struct IdkPtCtx {
     float sky[3] = {0.0f, 0.0f, 0.0f};
     DevBuf skyFaces;
     int skyFaceSize = 0;
+    DevBuf texPixels, texRecs, srgbLut;   // material textures (RGBA8 base levels), their records, sRGB decode table
 
     // present chain: bloom mip chains (rgba16f), AgX constants, RGBA8 frame
     DevBuf bloomDown, bloomUp, postConsts, ldr;
@@ -179,7 +180,7 @@ static int configure_launches(IdkPtCtx* ctx) {
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_rays, IDK_BLOCK, ctx->stackBytes));
     ctx->traceRaysBlocks = std::max(1, n) * ctx->smCount;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade, IDK_BLOCK, 0));
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_shade<false>, IDK_BLOCK, 0));
     ctx->shadeBlocks = std::max(1, n) * ctx->smCount;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_compact, IDK_BLOCK, 0));
     ctx->compactBlocks = std::max(1, std::min(n, 4)) * ctx->smCount;
@@ -195,7 +196,8 @@ static int configure_launches(IdkPtCtx* ctx) {
             cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_traverse2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(k_shade, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_compact, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_raygen, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_accumulate, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -280,6 +282,12 @@ static int relayout_treelet(const GpuBlasNode* src, uint32_t nodeCount, uint32_t
 // code, never a device fault): child pairs in range, even, and behind their parent (the builder emits DFS order, which
 // also rules out cycles); leaf ranges inside the BLAS's triangle range; and the traversal stack the kernels will need
 // (BLAS.ComputeRequiredStackSize, Bvh/BLAS.cs:672-702) must fit BlasStackSize. Returns nullptr or an error text.
+static const char* validate_material_textures(const GpuMaterial& m, uint64_t textureCount, const char* msg) {
+    const uint64_t h[5] = {m.BaseColorTexture, m.MetallicRoughnessTexture, m.NormalTexture, m.EmissiveTexture, m.TransmissionTexture};
+    for (int i = 0; i < 5; i++) if (h[i] > textureCount) return msg;
+    return nullptr;
+}
+
 static const char* validate_blas(const GpuBlasNode* nodes, const GpuBlasDesc& d, int blasStackSize) {
     const int n = d.NodeCount;
     if (n < 4 || (n & 1)) return "idkpt_set_scene: BLAS node count must be even and >= 4";
@@ -437,11 +445,19 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     for (uint64_t i = 0; i < s->MeshCount; i++)
         if (s->Meshes[i].MaterialId < 0 || (uint64_t)s->Meshes[i].MaterialId >= s->MaterialCount)
             return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuMesh.MaterialId out of range");
-    for (uint64_t i = 0; i < s->MaterialCount; i++) {
-        const GpuMaterial& m = s->Materials[i];
-        if (m.BaseColorTexture || m.MetallicRoughnessTexture || m.NormalTexture || m.EmissiveTexture || m.TransmissionTexture)
-            return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_scene: non-null texture handles are not supported yet (use 0 = 1x1 white)");
+    if (s->TextureCount && !s->Textures) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: TextureCount without Textures");
+    for (uint64_t i = 0; i < s->TextureCount; i++) {
+        const IdkPtTextureDesc& t = s->Textures[i];
+        if (!t.Pixels || t.Width < 1 || t.Height < 1 || t.Width > 16384 || t.Height > 16384) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: texture without pixels or with an invalid size");
+        if (t.Format != IDKPT_TEX_RGBA8_UNORM && t.Format != IDKPT_TEX_RGBA8_SRGB) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_scene: texture format not supported (RGBA8 unorm / sRGB only; transcode BCn on the host)");
+        for (int k = 0; k < 2; k++) {
+            const int wm = k ? t.WrapT : t.WrapS;
+            if (wm != 10497 && wm != 33071 && wm != 33648) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: texture wrap mode must be REPEAT, CLAMP_TO_EDGE or MIRRORED_REPEAT");
+        }
     }
+    for (uint64_t i = 0; i < s->MaterialCount; i++)
+        if (const char* err = validate_material_textures(s->Materials[i], s->TextureCount, "idkpt_set_scene: material texture handle outside the texture table (0 = white, k = Textures[k-1])"))
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, err);
 
     int rc;
     // nodes and triangle records share one allocation ("bvh"): [nodes | triRec], so that one L2 access-policy window covers both
@@ -472,6 +488,27 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     if ((rc = upload(ctx, ctx->vertices, s->Vertices, s->VertexCount * sizeof(GpuVertex)))) return rc;
     if ((rc = upload(ctx, ctx->lights, s->Lights, s->LightCount * sizeof(GpuLight)))) return rc;
     if ((rc = upload(ctx, ctx->tlas, s->TlasNodes, s->UseTlas ? s->TlasNodeCount * sizeof(GpuTlasNode) : 0))) return rc;
+    {   // material textures: all base levels in one allocation, 256-byte aligned; records point into it
+        std::vector<size_t> off(s->TextureCount + 1, 0);
+        for (uint64_t i = 0; i < s->TextureCount; i++) off[i + 1] = off[i] + ((((size_t)s->Textures[i].Width * s->Textures[i].Height * 4) + 255) & ~(size_t)255);
+        CK(ensure(ctx->texPixels, std::max<size_t>(off[s->TextureCount], 16)));
+        std::vector<TexRec> recs(s->TextureCount);
+        for (uint64_t i = 0; i < s->TextureCount; i++) {
+            const IdkPtTextureDesc& t = s->Textures[i];
+            CK(cudaMemcpyAsync((char*)ctx->texPixels.p + off[i], t.Pixels, (size_t)t.Width * t.Height * 4, cudaMemcpyHostToDevice, ctx->stream));
+            recs[i].px = (const uchar4*)((char*)ctx->texPixels.p + off[i]);
+            recs[i].w = t.Width; recs[i].h = t.Height; recs[i].wrapS = t.WrapS; recs[i].wrapT = t.WrapT;
+            recs[i].srgb = t.Format == IDKPT_TEX_RGBA8_SRGB ? 1 : 0; recs[i].pad = 0;
+        }
+        if ((rc = upload(ctx, ctx->texRecs, recs.data(), recs.size() * sizeof(TexRec)))) return rc;
+        float lut[256];   // GL_SRGB8 decode (OpenGL 4.6 spec 8.24), evaluated in double and rounded once
+        for (int i = 0; i < 256; i++) {
+            const double cs = i / 255.0;
+            lut[i] = (float)(cs <= 0.04045 ? cs / 12.92 : pow((cs + 0.055) / 1.055, 2.4));
+        }
+        if ((rc = upload(ctx, ctx->srgbLut, lut, sizeof(lut)))) return rc;
+        CK(cudaStreamSynchronize(ctx->stream));   // recs / lut are locals
+    }
 
     // triangle vertex ids must index the position / vertex arrays
     // (checked on the host copy: cheap relative to the BVH build that produced it)
@@ -520,6 +557,9 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     sc.treeletNodes = ctx->treeletNodes;
     sc.vtxFrame = (const float4*)ctx->vtxFrame.p;
     sc.surfRec = (const float4*)ctx->surfRec.p;
+    sc.textures = (const TexRec*)ctx->texRecs.p;
+    sc.textureCount = (uint32_t)s->TextureCount;
+    sc.srgbLut = (const float*)ctx->srgbLut.p;
     ctx->counts = *s;
     ctx->hostDescs.assign(s->BlasDescs, s->BlasDescs + s->BlasDescCount);
     ctx->nodeBytes = nodeBytes;
@@ -587,8 +627,8 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
     if (which == IDKPT_ARRAY_MATERIALS) {
         const GpuMaterial* m = (const GpuMaterial*)data;
         for (uint64_t i = 0; i < count; i++)
-            if (m[i].BaseColorTexture || m[i].MetallicRoughnessTexture || m[i].NormalTexture || m[i].EmissiveTexture || m[i].TransmissionTexture)
-                return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_update_range: non-null texture handles are not supported yet");
+            if (const char* err = validate_material_textures(m[i], ctx->counts.TextureCount, "idkpt_update_range: material texture handle outside the texture table"))
+                return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, err);
     }
     CK(cudaMemcpyAsync((char*)b->p + first * elem, data, count * elem, cudaMemcpyHostToDevice, ctx->stream));
     if ((which == IDKPT_ARRAY_MESHES || which == IDKPT_ARRAY_MATERIALS) && ctx->counts.MeshCount) {
@@ -803,7 +843,8 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             sa.lastBounce = last ? 1 : 0;
             sa.outputAovs = aovs ? 1 : 0;
             e0 = ev.begin();
-            k_shade<<<ctx->shadeBlocks, IDK_BLOCK, 0, ctx->stream>>>(sa);
+            if (ctx->sc.textureCount) k_shade<true><<<ctx->shadeBlocks, IDK_BLOCK, 0, ctx->stream>>>(sa);
+            else k_shade<false><<<ctx->shadeBlocks, IDK_BLOCK, 0, ctx->stream>>>(sa);
             launches++;
             if (!last) {
                 CompactArgs ca;

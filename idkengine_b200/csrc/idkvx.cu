@@ -155,6 +155,11 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
     for (uint64_t i = 0; i < s->MeshCount; i++)
         if (s->Meshes[i].MaterialId < 0 || (uint64_t)s->Meshes[i].MaterialId >= s->MaterialCount)
             return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_set_scene: GpuMesh.MaterialId out of range");
+    for (uint64_t i = 0; i < s->MaterialCount; i++) {
+        const GpuMaterial& m = s->Materials[i];
+        if (m.BaseColorTexture || m.MetallicRoughnessTexture || m.NormalTexture || m.EmissiveTexture || m.TransmissionTexture)
+            return vfail(ctx, IDKPT_ERR_UNSUPPORTED, "idkvx_set_scene: the voxeliser takes factor-only materials (texture handles must be 0)");
+    }
     int rc;
     if ((rc = vupload(ctx, &ctx->dPositions, s->VertexPositions, s->VertexPositionCount * sizeof(PackedVec3)))) return rc;
     if ((rc = vupload(ctx, &ctx->dVertices, s->Vertices, s->VertexCount * sizeof(GpuVertex)))) return rc;

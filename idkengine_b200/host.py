@@ -175,6 +175,7 @@ class Scene:
         self.blas_instances = np.zeros(0, gt.GpuBlasInstance)
         self.tlas_nodes = np.zeros(0, gt.GpuTlasNode)
         self.lights = np.zeros(0, gt.GpuLight)
+        self.textures = []             # dict(pixels [H, W, 4] uint8, srgb, wrap_s, wrap_t); material handle k = textures[k - 1]
         self.use_tlas = 0
         self.blas_stack_size = 1
         self.source_triangle_count = 0
@@ -254,6 +255,14 @@ class Scene:
             L.idkhost_tlas_build(boxes.ctypes.data, n, self.tlas_nodes.ctypes.data, search_radius)
         self.use_tlas = 1 if use else 0
         return self
+
+    def add_texture(self, pixels, srgb=False, wrap_s=10497, wrap_t=10497):
+        """Registers an RGBA8 image and returns the handle to store in a GpuMaterial texture slot (ModelLoader's bindless
+        handle, ModelLoader.cs:985-1000; here an index into IdkPtSceneDesc.Textures, 0 = 1x1 white)."""
+        pixels = np.ascontiguousarray(pixels, np.uint8)
+        assert pixels.ndim == 3 and pixels.shape[2] == 4
+        self.textures.append(dict(pixels=pixels, srgb=bool(srgb), wrap_s=int(wrap_s), wrap_t=int(wrap_t)))
+        return len(self.textures)
 
     def add_light(self, position, color, radius):
         """LightManager.AddLight (SRC/Render/LightManager.cs) -> GpuLight in UBO 2."""

@@ -303,6 +303,76 @@ def multi_blas(threads=None):
     return scene, cam
 
 
+
+# --------------------------------------------------------------------------- textured room (material textures)
+def _checker(n, cells, a, b, alpha_a=255, alpha_b=255, seed=0):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:n, 0:n]
+    on = (((xx * cells) // n + (yy * cells) // n) % 2).astype(bool)
+    img = np.zeros((n, n, 4), np.uint8)
+    img[..., :3] = np.where(on[..., None], np.array(a, np.uint8), np.array(b, np.uint8))
+    img[..., :3] = np.clip(img[..., :3].astype(np.int32) + rng.integers(-12, 13, (n, n, 3)), 0, 255)
+    img[..., 3] = np.where(on, alpha_a, alpha_b)
+    return img
+
+
+def textured_room(threads=None):
+    """A room whose materials use every texture slot of GpuMaterial (BaseColor sRGB with alpha, MetallicRoughness, Normal,
+    Emissive, Transmission), all three wrap modes and non-square / non-power-of-two sizes; texcoords run outside [0, 1]."""
+    scene = Scene()
+    rng = np.random.default_rng(5)
+    t_floor = scene.add_texture(_checker(64, 8, (200, 190, 170), (60, 50, 40), seed=1), srgb=True)
+    t_wall = scene.add_texture(_checker(48, 6, (120, 140, 200), (200, 120, 90), seed=2)[:32], srgb=True, wrap_s=33648, wrap_t=33071)
+    nrm = np.zeros((40, 56, 4), np.uint8)
+    yy, xx = np.mgrid[0:40, 0:56]
+    nrm[..., 0] = (127.5 + 90 * np.sin(xx * 0.6)).astype(np.uint8)
+    nrm[..., 1] = (127.5 + 90 * np.cos(yy * 0.5)).astype(np.uint8)
+    nrm[..., 2:] = 255
+    t_normal = scene.add_texture(nrm)
+    mr = rng.integers(0, 256, (16, 16, 4)).astype(np.uint8)
+    t_mr = scene.add_texture(mr, wrap_s=33071, wrap_t=33648)
+    t_cut = scene.add_texture(_checker(32, 4, (30, 160, 60), (30, 160, 60), alpha_a=255, alpha_b=20, seed=3), srgb=True)
+    t_blend = scene.add_texture(_checker(32, 2, (220, 60, 200), (60, 200, 220), alpha_a=200, alpha_b=90, seed=4), srgb=True)
+    t_emis = scene.add_texture(_checker(24, 3, (255, 220, 160), (10, 10, 10), seed=5), srgb=True)
+    t_trans = scene.add_texture(_checker(20, 5, (255, 255, 255), (40, 40, 40), seed=6))
+    specs = [
+        dict(color=(1.0, 1.0, 1.0)),                                              # 0 floor: base colour texture
+        dict(color=(0.9, 0.9, 0.9), metallic=1.0, roughness=1.0),                 # 1 wall: base + normal + metallic/roughness
+        dict(color=(1.0, 1.0, 1.0), cutoff=0.5),                                  # 2 cutout card
+        dict(color=(1.0, 1.0, 1.0, 0.9), cutoff=2.0),                             # 3 blended card
+        dict(color=(0.2, 0.2, 0.2), emissive=(9.0, 8.0, 6.0)),                    # 4 emissive panel
+        dict(color=(0.95, 0.95, 1.0), transmission=1.0, roughness=0.05, ior=1.45),  # 5 pane with a transmission texture
+        dict(color=(0.75, 0.75, 0.75)),                                           # 6 untextured ceiling / side walls
+        dict(color=(1, 1, 1), emissive=(14, 14, 14)),                             # 7 lamp
+    ]
+    meshes, mats = _materials(specs)
+    mats["BaseColorTexture"][0] = t_floor
+    mats["BaseColorTexture"][1], mats["NormalTexture"][1], mats["MetallicRoughnessTexture"][1] = t_wall, t_normal, t_mr
+    mats["BaseColorTexture"][2] = t_cut
+    mats["BaseColorTexture"][3] = t_blend
+    mats["EmissiveTexture"][4] = t_emis
+    mats["TransmissionTexture"][5] = t_trans
+    meshes["NormalMapStrength"][1] = 0.8
+    a = _Assembler()
+    a.add(grid([-3, 0, -3], [6, 0, 0], [0, 0, 6], 6, 6), 0)
+    a.add(grid([-3, 0, -3], [6, 0, 0], [0, 4, 0], 6, 4), 1)
+    a.add(quad([-1.6, 0.2, -1.0], [-0.4, 0.2, -1.0], [-0.4, 1.8, -1.0], [-1.6, 1.8, -1.0]), 2)
+    a.add(quad([0.3, 0.3, -0.4], [1.5, 0.3, -0.9], [1.5, 1.7, -0.9], [0.3, 1.7, -0.4]), 3)
+    a.add(quad([-2.9, 1.0, -2.0], [-2.9, 1.0, 0.0], [-2.9, 2.2, 0.0], [-2.9, 2.2, -2.0]), 4)
+    a.add(quad([-0.8, 0.1, 0.9], [0.8, 0.1, 0.9], [0.8, 1.5, 0.9], [-0.8, 1.5, 0.9]), 5)
+    a.add(quad([-3, 4, -3], [3, 4, -3], [3, 4, 3], [-3, 4, 3]), 6)
+    a.add(quad([-3, 0, -3], [-3, 0, 3], [-3, 4, 3], [-3, 4, -3]), 6)
+    a.add(quad([3, 0, 3], [3, 0, -3], [3, 4, -3], [3, 4, 3]), 6)
+    a.add(quad([-0.7, 3.98, -0.7], [0.7, 3.98, -0.7], [0.7, 3.98, 0.7], [-0.7, 3.98, 0.7]), 7)
+    pos = np.concatenate(a.pos)
+    uv = np.stack([pos[:, 0] * 0.61 + pos[:, 2] * 0.43 - 0.3, pos[:, 1] * 0.57 + pos[:, 2] * 0.29 - 0.7], 1).astype(np.float32)
+    model = Model(pos, np.concatenate(a.idx), np.concatenate(a.mesh), texcoords=uv, meshes=meshes, materials=mats, name="textured_room")
+    scene.add(model, threads=threads)
+    scene.add_light((1.5, 2.6, 1.2), (25.0, 24.0, 22.0), 0.25)
+    cam = dict(position=(0.2, 1.5, 4.6), view_dir=(-0.05, -0.08, -1.0), fov_y_deg=62.0)
+    return scene, cam
+
+
 # --------------------------------------------------------------------------- real Sponza (local only)
 REFERENCE_SPONZA = "/root/reference/IDKEngine/Resource/Models/SponzaCompressed/Sponza.gltf"
 

@@ -64,6 +64,21 @@ typedef struct IdkPtCreateInfo {
 /* Replaces the implicit SSBO bindings 4,5(vertices),8,9..: ModelManager.cs:103-119
  * (meshes, materials, vertices, positions, transforms) and BVH.cs:145-152,445-451
  * (nodes, triangles, descs, instances, tlas) plus LightManager.cs:80 (UBO 2). */
+/* Material textures. The reference stores 64-bit GL bindless sampler handles in GpuMaterial (GpuMaterial.cs:8-67); here a
+ * handle is an index into this table: 0 = the 1x1 white fallback (ModelLoader.cs:1855-1870), k > 0 = Textures[k-1]. Base
+ * level only: the path tracer's compute shaders sample lod 0 (Surface.glsl:57-60). Uncompressed RGBA8 as the loader
+ * creates for non-KTX images (BaseColor/Emissive sRGB, ModelLoader.cs:938-945); BCn/KTX2 sources are transcoded on the host.
+ * Channel use as in Surface.glsl:49-77: BaseColor rgba, MetallicRoughness r = metallic g = roughness, Normal rg,
+ * Emissive rgb, Transmission r. */
+typedef enum IdkPtTextureFormat { IDKPT_TEX_RGBA8_UNORM = 0, IDKPT_TEX_RGBA8_SRGB = 1 } IdkPtTextureFormat;
+typedef struct IdkPtTextureDesc {
+    const void* Pixels;       /* Width*Height*4 bytes, row 0 first (v = 0) */
+    int32_t Width, Height;
+    int32_t Format;           /* IdkPtTextureFormat */
+    int32_t WrapS, WrapT;     /* GL enums as in the glTF sampler: 10497 REPEAT, 33071 CLAMP_TO_EDGE, 33648 MIRRORED_REPEAT */
+    int32_t _pad0;
+} IdkPtTextureDesc;
+
 typedef struct IdkPtSceneDesc {
     const GpuBlasNode*      BlasNodes;       uint64_t BlasNodeCount;
     const GpuBlasTriangle*  BlasTriangles;   uint64_t BlasTriangleCount;
@@ -78,6 +93,7 @@ typedef struct IdkPtSceneDesc {
     const GpuLight*         Lights;          uint64_t LightCount;        /* <= 256 */
     int32_t UseTlas;        /* BVH.GpuUseTlas (BVH.cs:18-27); default 0 */
     int32_t BlasStackSize;  /* BVH.BlasStackSize (BVH.cs:29-45,559-567) = max RequiredStackSize */
+    const IdkPtTextureDesc* Textures; uint64_t TextureCount;             /* may be NULL/0: every material handle must then be 0 */
 } IdkPtSceneDesc;
 
 typedef enum IdkPtArrayId {

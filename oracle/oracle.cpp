@@ -570,6 +570,84 @@ static Surface GetDefaultSurface() {
     return s;
 }
 // Surface.glsl:49-77 with every sampler = 1x1 white (texture(...) == vec4(1)).
+// texture(sampler2D, uv) at lod 0 (compute shaders have no derivatives, Surface.glsl:57-60): explicit fp32 bilinear on the base
+// level, glTF wrap modes, sRGB decode before filtering. Handle 0 = 1x1 white, k = Textures[k-1] (include/idkpt.h).
+struct Vec4 { float x, y, z, w; };
+static inline int TexWrap(int i, int n, int mode) {
+    if (mode == 33071) return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+    if (mode == 33648) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
+    int m = i % n;
+    return m < 0 ? m + n : m;
+}
+static const float* SrgbLut() {
+    static float lut[256];
+    static bool init = false;
+    if (!init) {
+        for (int i = 0; i < 256; i++) {
+            const double cs = i / 255.0;
+            lut[i] = (float)(cs <= 0.04045 ? cs / 12.92 : pow((cs + 0.055) / 1.055, 2.4));
+        }
+        init = true;
+    }
+    return lut;
+}
+static inline Vec4 TexFetch(const IdkPtTextureDesc& t, int x, int y) {
+    const uint8_t* c = (const uint8_t*)t.Pixels + 4 * ((size_t)y * t.Width + x);
+    if (t.Format == IDKPT_TEX_RGBA8_SRGB) { const float* lut = SrgbLut(); return {lut[c[0]], lut[c[1]], lut[c[2]], (float)c[3] / 255.0f}; }
+    return {(float)c[0] / 255.0f, (float)c[1] / 255.0f, (float)c[2] / 255.0f, (float)c[3] / 255.0f};
+}
+static inline Vec4 TexLerp(Vec4 a, Vec4 b, float t) {
+    const float s = 1.0f - t;
+    return {a.x * s + b.x * t, a.y * s + b.y * t, a.z * s + b.z * t, a.w * s + b.w * t};
+}
+static Vec4 TexSample(const IdkPtSceneDesc& d, uint64_t handle, float u, float v) {
+    if (handle == 0) return {1.0f, 1.0f, 1.0f, 1.0f};
+    const IdkPtTextureDesc& t = d.Textures[handle - 1];
+    if (t.WrapS == 10497) u = u - floorf(u);
+    if (t.WrapT == 10497) v = v - floorf(v);
+    const float px = u * (float)t.Width - 0.5f, py = v * (float)t.Height - 0.5f;
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float fx = px - fx0, fy = py - fy0;
+    const int x0 = TexWrap((int)fx0, t.Width, t.WrapS), x1 = TexWrap((int)fx0 + 1, t.Width, t.WrapS);
+    const int y0 = TexWrap((int)fy0, t.Height, t.WrapT), y1 = TexWrap((int)fy0 + 1, t.Height, t.WrapT);
+    const Vec4 a = TexLerp(TexFetch(t, x0, y0), TexFetch(t, x1, y0), fx);
+    const Vec4 b = TexLerp(TexFetch(t, x0, y1), TexFetch(t, x1, y1), fx);
+    return TexLerp(a, b, fy);
+}
+static inline bool MaterialHasTextures(const GpuMaterial& m) {
+    return (m.BaseColorTexture | m.MetallicRoughnessTexture | m.NormalTexture | m.EmissiveTexture | m.TransmissionTexture) != 0;
+}
+
+static Surface GetSurface(const GpuMaterial& m);
+// GetSurface(gpuMaterial, uv), Surface.glsl:49-77
+static Surface GetSurface(const IdkPtSceneDesc& d, const GpuMaterial& m, float u, float v) {
+    if (!MaterialHasTextures(m)) return GetSurface(m);
+    Surface s;
+    const uint32_t c = m.BaseColorFactor;
+    const Vec4 base = TexSample(d, m.BaseColorTexture, u, v);
+    s.Albedo = {base.x * ((float)(c & 255u) / 255.0f), base.y * ((float)((c >> 8) & 255u) / 255.0f), base.z * ((float)((c >> 16) & 255u) / 255.0f)};
+    s.Alpha = base.w * ((float)((c >> 24) & 255u) / 255.0f);
+    const Vec4 nt = TexSample(d, m.NormalTexture, u, v);
+    s.Normal = {nt.x * 2.0f - 1.0f, nt.y * 2.0f - 1.0f, sqrtf(fmaxf(1.0f - (nt.x * nt.x + nt.y * nt.y), 0.0f))};   // ReconstructPackedNormal, Compression.glsl:78-84
+    const Vec4 et = TexSample(d, m.EmissiveTexture, u, v);
+    s.Emissive = {et.x * m.EmissiveFactor[0], et.y * m.EmissiveFactor[1], et.z * m.EmissiveFactor[2]};
+    s.Absorbance = V(m.Absorbance);
+    const Vec4 mr = TexSample(d, m.MetallicRoughnessTexture, u, v);
+    s.Metallic = mr.x * m.MetallicFactor;
+    s.Roughness = mr.y * m.RoughnessFactor;
+    s.Transmission = TexSample(d, m.TransmissionTexture, u, v).x * m.TransmissionFactor;
+    s.IOR = m.IOR;
+    s.AlphaCutoff = m.AlphaCutoff;
+    s.IsVolumetric = m.IsVolumetric != 0;
+    s.TintOnTransmissive = true;
+    return s;
+}
+static inline void InterpTexCoord(const IdkPtSceneDesc& d, const GpuBlasTriangle& tri, float b0, float b1, float b2, float& u, float& v) {
+    const GpuVertex& v0 = d.Vertices[tri.X]; const GpuVertex& v1 = d.Vertices[tri.Y]; const GpuVertex& v2 = d.Vertices[tri.Z];
+    u = (v0.TexCoord[0] * b0 + v1.TexCoord[0] * b1) + v2.TexCoord[0] * b2;   // Interpolate(), Math.glsl:54-57
+    v = (v0.TexCoord[1] * b0 + v1.TexCoord[1] * b1) + v2.TexCoord[1] * b2;
+}
+
 static Surface GetSurface(const GpuMaterial& m) {
     Surface s;
     uint32_t c = m.BaseColorFactor;
@@ -717,7 +795,8 @@ static bool ShadeTraceRay(const Scene& s, const Settings& st, Rng& rng, WRay& ra
             const GpuVertex& v1 = s.d.Vertices[tri.Y];
             const GpuVertex& v2 = s.d.Vertices[tri.Z];
             vec3 bary = {hitInfo.bx, hitInfo.by, 1.0f - hitInfo.bx - hitInfo.by};
-            // interpTexCoord is computed by the reference but only feeds the (constant) texture fetches.
+            float texU, texV;
+            InterpTexCoord(s.d, tri, bary.x, bary.y, bary.z, texU, texV);
             vec3 n0 = DecompressSR11G11B10(v0.Normal), n1 = DecompressSR11G11B10(v1.Normal), n2 = DecompressSR11G11B10(v2.Normal);
             vec3 interpNormal = normalize((n0 * bary.x + n1 * bary.y) + n2 * bary.z);
             vec3 t0 = DecompressSR11G11B10(v0.Tangent), t1 = DecompressSR11G11B10(v1.Tangent), t2 = DecompressSR11G11B10(v2.Tangent);
@@ -727,7 +806,7 @@ static bool ShadeTraceRay(const Scene& s, const Settings& st, Rng& rng, WRay& ra
             const GpuMesh& mesh = s.d.Meshes[tri.MeshId];
             const GpuMaterial& material = s.d.Materials[mesh.MaterialId];
 
-            surface = GetSurface(material);
+            surface = GetSurface(s.d, material, texU, texV);
             SurfaceApplyModificatons(surface, mesh);
 
             float alphaCutoff = (surface.AlphaCutoff == 2.0f) ? GetRandomFloat01(rng) : surface.AlphaCutoff;
@@ -1315,7 +1394,9 @@ ORACLE_API int oracle_shadows_ray_traced(const IdkPtSceneDesc* scene, const GpuP
                         }
                         const GpuBlasTriangle& tri = s.d.BlasTriangles[hitInfo.TriangleId];
                         const GpuMesh& mesh = s.d.Meshes[tri.MeshId];
-                        Surface surface = GetSurface(s.d.Materials[mesh.MaterialId]);
+                        float texU, texV;
+                        InterpTexCoord(s.d, tri, hitInfo.bx, hitInfo.by, 1.0f - hitInfo.bx - hitInfo.by, texU, texV);
+                        Surface surface = GetSurface(s.d, s.d.Materials[mesh.MaterialId], texU, texV);
                         SurfaceApplyModificatons(surface, mesh);
                         if (surface.AlphaCutoff == 2.0f) thisVisibility *= 1.0f - surface.Alpha;
                         else if (surface.Alpha > surface.AlphaCutoff) thisVisibility = 0.0f;
@@ -1404,3 +1485,15 @@ ORACLE_API void oracle_blas_refit(GpuBlasNode* allNodes, const GpuBlasDesc* desc
 
 } // extern "C"
 #include "oracle_post.inc"
+
+extern "C" {
+// Test hook: TexSample of one texture at n (u, v) points -> rgba floats.
+ORACLE_API void oracle_tex_sample(const IdkPtTextureDesc* tex, const float* uv, uint64_t n, float* out) {
+    IdkPtSceneDesc d = {};
+    d.Textures = tex; d.TextureCount = 1;
+    for (uint64_t i = 0; i < n; i++) {
+        const Vec4 c = TexSample(d, 1, uv[2 * i], uv[2 * i + 1]);
+        out[4 * i] = c.x; out[4 * i + 1] = c.y; out[4 * i + 2] = c.z; out[4 * i + 3] = c.w;
+    }
+}
+}

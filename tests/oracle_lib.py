@@ -132,6 +132,18 @@ def post_process(result, settings=None, want_bloom=False, threads=None):
     return (out, bloom) if want_bloom else out
 
 
+def tex_sample(pixels, uv, srgb=False, wrap_s=10497, wrap_t=10497):
+    px = np.ascontiguousarray(pixels, np.uint8)
+    uv = np.ascontiguousarray(uv, np.float32)
+    t = capi.IdkPtTextureDesc(px.ctypes.data, px.shape[1], px.shape[0], 1 if srgb else 0, wrap_s, wrap_t, 0)
+    out = np.zeros((len(uv), 4), np.float32)
+    L = lib()
+    L.oracle_tex_sample.restype = None
+    L.oracle_tex_sample.argtypes = [ctypes.POINTER(capi.IdkPtTextureDesc), ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+    L.oracle_tex_sample(ctypes.byref(t), uv.ctypes.data, len(uv), out.ctypes.data)
+    return out
+
+
 def brute_force(scene, rays, threads=None):
     d, keep = capi.scene_desc(scene)
     out = np.zeros(len(rays), gt.IdkPtHit)

@@ -1,0 +1,135 @@
+"""Material textures (the constant-texture restriction of round 1 lifted): Surface.glsl:49-77 with real samplers."""
+import copy
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from idkengine_b200 import capi, scenes
+
+
+@pytest.fixture(scope="module")
+def textured():
+    return scenes.textured_room(threads=1)
+
+
+def ref_sample(px, uv, srgb, wrap_s, wrap_t):
+    """float64 restatement of GL bilinear sampling at lod 0 with the three wrap modes."""
+    h, w = px.shape[:2]
+    tex = px.astype(np.float64) / 255.0
+    if srgb:
+        c = tex[..., :3]
+        tex[..., :3] = np.where(c <= 0.04045, c / 12.92, ((c + 0.055) / 1.055) ** 2.4)
+
+    def wrap(i, n, mode):
+        if mode == 33071:
+            return np.clip(i, 0, n - 1)
+        if mode == 33648:
+            m = np.mod(i, 2 * n)
+            return np.where(m < n, m, 2 * n - 1 - m)
+        return np.mod(i, n)
+
+    u, v = uv[:, 0].astype(np.float64), uv[:, 1].astype(np.float64)
+    x, y = u * w - 0.5, v * h - 0.5
+    x0, y0 = np.floor(x), np.floor(y)
+    fx, fy = (x - x0)[:, None], (y - y0)[:, None]
+    xa, xb = wrap(x0.astype(int), w, wrap_s), wrap(x0.astype(int) + 1, w, wrap_s)
+    ya, yb = wrap(y0.astype(int), h, wrap_t), wrap(y0.astype(int) + 1, h, wrap_t)
+    top = tex[ya, xa] * (1 - fx) + tex[ya, xb] * fx
+    bot = tex[yb, xa] * (1 - fx) + tex[yb, xb] * fx
+    return top * (1 - fy) + bot * fy
+
+
+@pytest.mark.parametrize("srgb", [False, True])
+@pytest.mark.parametrize("wrap_s,wrap_t", [(10497, 10497), (33071, 33648), (33648, 33071)])
+def test_oracle_sampling_matches_gl_rules(srgb, wrap_s, wrap_t):
+    rng = np.random.default_rng(2)
+    px = rng.integers(0, 256, (7, 12, 4)).astype(np.uint8)
+    uv = rng.uniform(-2.5, 3.5, (4000, 2)).astype(np.float32)
+    got = ol.tex_sample(px, uv, srgb, wrap_s, wrap_t)
+    want = ref_sample(px, uv, srgb, wrap_s, wrap_t)
+    assert np.abs(got - want).max() < 2e-5      # texel-boundary rounding of u*w in fp32 moves a sample by at most ~1e-6 texel
+    centre = np.array([[(3 + 0.5) / 12, (2 + 0.5) / 7]], np.float32)   # texel centre: exactly that texel
+    c = ol.tex_sample(px, centre, False, wrap_s, wrap_t)[0]
+    assert np.allclose(c, px[2, 3] / 255.0, atol=1e-6)
+
+
+def test_oracle_textures_change_the_image(textured):
+    scene, cam = textured
+    w, h = 80, 60
+    frame = scenes.camera_frame(cam, w, h)
+    s = capi.default_settings()
+    s.OutputAOVs = 1
+    a = ol.path_trace(scene, frame, s, w, h)
+    plain = copy.deepcopy(scene)
+    for f in ("BaseColorTexture", "MetallicRoughnessTexture", "NormalTexture", "EmissiveTexture", "TransmissionTexture"):
+        plain.materials[f] = 0
+    b = ol.path_trace(plain, frame, s, w, h)
+    assert not np.array_equal(a.albedo, b.albedo) and not np.array_equal(a.normal, b.normal)
+    # an all-white texture is the reference's fallback: same image as handle 0
+    white = copy.deepcopy(plain)
+    hnd = white.add_texture(np.full((4, 4, 4), 255, np.uint8), srgb=True)
+    white.materials["BaseColorTexture"][0] = hnd
+    white.materials["EmissiveTexture"][4] = hnd
+    c = ol.path_trace(white, frame, s, w, h)
+    assert np.allclose(c.result, b.result, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sorting,lights", [(0, 1), (1, 0)])
+def test_textured_path_trace_bit_exact(textured, sorting, lights):
+    from idkengine_b200.pathtracer import PathTracer
+    scene, cam = textured
+    w, h = 160, 120
+    frame = scenes.camera_frame(cam, w, h)
+    s = capi.default_settings()
+    s.OutputAOVs, s.DoRaySorting, s.CollectStats = 1, sorting, 1
+    s.Gpu.DoTraceLights = lights
+    with PathTracer(w, h, s) as pt:
+        pt.SetScene(scene)
+        pt.SetSky((0.6, 0.7, 0.9))
+        pt.SetFrame(frame)
+        st = [pt.Compute() for _ in range(2)]
+        g = dict(result=pt.Result.copy(), albedo=pt.AlbedoTexture.copy(), normal=pt.NormalTexture.copy())
+    res = np.zeros((h, w, 4), np.float32)
+    alb, nrm = np.zeros_like(res), np.zeros_like(res)
+    o = ol.path_trace(scene, frame, s, w, h, result=res, albedo=alb, normal=nrm)
+    o = ol.path_trace(scene, frame, s, w, h, accumulated=o.accumulated, result=res, albedo=alb, normal=nrm)
+    for name, img in (("result", res), ("albedo", alb), ("normal", nrm)):
+        assert np.array_equal(g[name].view(np.uint32), img.view(np.uint32)), name
+    assert st[-1].Rays == o.stats.Rays and st[-1].NodePairFetches == o.stats.NodePairFetches
+
+
+@pytest.mark.gpu
+def test_textured_shadows_bit_exact(textured):
+    from idkengine_b200.pathtracer import PathTracer
+    scene, cam = textured
+    w, h = 160, 120
+    frame = scenes.camera_frame(cam, w, h)
+    depth, nrg, _ = ol.synth_gbuffer(scene, frame, w, h)
+    with PathTracer(64, 64) as pt:
+        pt.SetScene(scene)
+        g, _ = pt.ShadowsRayTraced(frame, depth, nrg, 0, samples=2)
+    o = ol.shadows_ray_traced(scene, frame, depth, nrg, 0, samples=2)
+    assert np.array_equal(g.view(np.uint32), o.view(np.uint32))
+    partial = g[(g > 0.01) & (g < 0.99)]
+    assert partial.size > 0                          # alpha-blended / cut-out cards give fractional visibility
+
+
+@pytest.mark.gpu
+def test_texture_handle_validation(textured):
+    from idkengine_b200.pathtracer import PathTracer
+    scene = copy.deepcopy(textured[0])
+    scene.materials["NormalTexture"][0] = len(scene.textures) + 1
+    with PathTracer(32, 32) as pt:
+        with pytest.raises(RuntimeError, match="texture"):
+            pt.SetScene(scene)
+        good = textured[0]
+        pt.SetScene(good)
+        bad = good.materials[:1].copy()
+        bad["EmissiveTexture"] = 99
+        with pytest.raises(RuntimeError, match="texture"):
+            pt.UpdateRange(capi.IDKPT_ARRAY_MATERIALS, 0, bad)
+        ok = good.materials[:1].copy()
+        ok["BaseColorTexture"] = 2
+        pt.UpdateRange(capi.IDKPT_ARRAY_MATERIALS, 0, ok)
