@@ -49,6 +49,9 @@ struct IdkPtCtx {
     int skyFaceSize = 0;
     DevBuf texPixels, texRecs, srgbLut;   // material textures (RGBA8 base levels), their records, sRGB decode table
 
+    // host-array entry points (trace_rays, shadows): device staging buffers, kept between calls
+    DevBuf scratch[3];
+
     // present chain: bloom mip chains (rgba16f), AgX constants, RGBA8 frame
     DevBuf bloomDown, bloomUp, postConsts, ldr;
 
@@ -397,7 +400,9 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
                      &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->vtxFrame, &ctx->surfRec, &ctx->state, &ctx->aov, &ctx->alive[0],
                      &ctx->alive[1], &ctx->survivors, &ctx->keysTmp, &ctx->sortedAlive, &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
                      &ctx->aovNormalFinal, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
-                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->countLog, &ctx->skyFaces};
+                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->countLog, &ctx->skyFaces,
+                     &ctx->texPixels, &ctx->texRecs, &ctx->srgbLut, &ctx->bloomDown, &ctx->bloomUp, &ctx->postConsts, &ctx->ldr,
+                     &ctx->unskinned, &ctx->joints, &ctx->refitParents, &ctx->refitLocks, &ctx->scratch[0], &ctx->scratch[1], &ctx->scratch[2]};
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ctx->sortScratch);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
@@ -1340,7 +1345,7 @@ IDKPT_API int idkpt_shadows_ray_traced(IdkPtCtx* ctx, const GpuPerFrameData* fra
     CK(cudaSetDevice(ctx->device));
     if (kernelMs) *kernelMs = 0.0f;
     const size_t n = (size_t)width * height;
-    DevBuf dDepth, dN, dVis;
+    DevBuf &dDepth = ctx->scratch[0], &dN = ctx->scratch[1], &dVis = ctx->scratch[2];
     int rc = IDKPT_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     do {
@@ -1365,7 +1370,6 @@ IDKPT_API int idkpt_shadows_ray_traced(IdkPtCtx* ctx, const GpuPerFrameData* fra
     } while (0);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    release(dDepth); release(dN); release(dVis);
     return rc;
 }
 
@@ -1376,7 +1380,7 @@ static int trace_rays_impl(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, 
     if (kernelMs) *kernelMs = 0.0f;
     if (count == 0) return IDKPT_OK;
     CK(cudaSetDevice(ctx->device));
-    DevBuf dr, dh, dt;
+    DevBuf &dr = ctx->scratch[0], &dh = ctx->scratch[1], &dt = ctx->scratch[2];
     int rc = IDKPT_OK;
     cudaEvent_t e0 = nullptr, e1 = nullptr;
     do {
@@ -1403,7 +1407,6 @@ static int trace_rays_impl(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, 
     } while (0);
     if (e0) cudaEventDestroy(e0);
     if (e1) cudaEventDestroy(e1);
-    release(dr); release(dh); release(dt);
     return rc;
 }
 
