@@ -320,6 +320,12 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["sampled_over"] = f"the {args.steps} timed steps + {extra_steps} identical untimed steps (nvidia-smi -lms 100)"
+    per_rank = None
+    if world > 1:      # per-rank device times: shows tile imbalance / a slow GPU behind the max-over-ranks figure
+        mine = {"rank": rank, "total": dev_ms / args.steps, "traverse": trav_ms / args.steps, "shade": shade_ms / args.steps,
+                "gather": gather_ms / args.steps, "rays": rays // args.steps}
+        per_rank = [None] * world
+        dist.all_gather_object(per_rank, mine)
     total_rays = reduce(rays, SUM)
     total_launches = int(reduce(launches, SUM))
     e2e_ms = reduce(e2e_ms, MAX)
@@ -348,6 +354,8 @@ def run_ours(args, rank, world, local_rank):
             "gpu_launches": total_launches,
             "clocks": clocks,
         }
+        if per_rank is not None:
+            line["per_rank_ms"] = per_rank
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(scene, frame, args)
         print(json.dumps(line))
