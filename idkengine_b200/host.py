@@ -56,6 +56,16 @@ def lib():
         L.idkhost_blas_copy.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
         L.idkhost_blas_free.restype = None
         L.idkhost_blas_free.argtypes = [ctypes.c_void_p]
+        L.idkhost_hash64.restype = ctypes.c_uint64
+        L.idkhost_hash64.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
+        L.idkhost_cache_save.restype = ctypes.c_int32
+        L.idkhost_cache_save.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint32]
+        L.idkhost_cache_open.restype = ctypes.c_int32
+        L.idkhost_cache_open.argtypes = [ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(ctypes.c_void_p)]
+        L.idkhost_cache_array.restype = ctypes.c_void_p
+        L.idkhost_cache_array.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(ctypes.c_uint64)]
+        L.idkhost_cache_close.restype = None
+        L.idkhost_cache_close.argtypes = [ctypes.c_void_p]
         L.idkhost_transform_box.restype = None
         L.idkhost_transform_box.argtypes = [ctypes.c_void_p] * 5
         L.idkhost_tlas_build.restype = None
@@ -93,6 +103,67 @@ def build_blas(positions, triangles, presplit=True, threads=None, settings=None)
                     sah=float(L.idkhost_blas_sah(h)))
     finally:
         L.idkhost_blas_free(h)
+
+
+# --------------------------------------------------------------------------- on-disk BLAS cache (include/idkhost_cache.h)
+BUILDER_VERSION = 1          # bump when host/bvh_build.cpp changes its output
+CACHE_BLAS_NODES, CACHE_BLAS_TRIANGLES, CACHE_BUILD_INFO = 1, 2, 100
+CACHE_OK, CACHE_ERR_IO, CACHE_ERR_FORMAT, CACHE_ERR_KEY, CACHE_ERR_CHECKSUM = 0, -1, -2, -3, -4
+
+
+class IdkHostCacheArray(ctypes.Structure):
+    _fields_ = [("Id", ctypes.c_uint32), ("ElemSize", ctypes.c_uint32), ("Count", ctypes.c_uint64), ("Data", ctypes.c_void_p)]
+
+
+def hash64(arr, seed=0):
+    arr = np.ascontiguousarray(arr)
+    return int(lib().idkhost_hash64(arr.ctypes.data, arr.nbytes, seed))
+
+
+def blas_source_key(model_positions, model_indices, tri_mesh, presplit, settings=None):
+    """Hash of everything the builder's output depends on (not the thread count: the build is deterministic)."""
+    s = settings or default_build_settings()
+    blob = np.array([BUILDER_VERSION, s.StopSplittingThreshold, s.MaxLeafTriangleCount, s.StackOptThreshold, 1 if presplit else 0], np.int64)
+    fl = np.array([s.TriangleCost, s.StackOptSahIncreaseAcceptance, s.SplitFactor], np.float32)
+    h = hash64(blob)
+    h = hash64(fl, h)
+    h = hash64(np.ascontiguousarray(model_positions, np.float32), h)
+    h = hash64(np.ascontiguousarray(model_indices, np.uint32), h)
+    return hash64(np.ascontiguousarray(tri_mesh, np.int32), h)
+
+
+def cache_save(path, key, b):
+    """b: build_blas result with BLAS-local triangle vertex ids (relative to the model's first vertex) and mesh ids."""
+    info = np.array([b["required_stack_size"], b["fragment_count"]], np.float64)
+    info = np.concatenate([info, [b["sah"]]])
+    keep = [np.ascontiguousarray(b["nodes"]), np.ascontiguousarray(b["triangles"]), info]
+    arr = (IdkHostCacheArray * 3)(
+        IdkHostCacheArray(CACHE_BLAS_NODES, 32, len(keep[0]), keep[0].ctypes.data),
+        IdkHostCacheArray(CACHE_BLAS_TRIANGLES, 16, len(keep[1]), keep[1].ctypes.data),
+        IdkHostCacheArray(CACHE_BUILD_INFO, 8, len(info), info.ctypes.data))
+    return int(lib().idkhost_cache_save(os.fsencode(path), key, ctypes.addressof(arr), 3))
+
+
+def cache_load(path, key):
+    """Returns (rc, build-result dict or None); the arrays are copied out of the mapping."""
+    L = lib()
+    view = ctypes.c_void_p()
+    rc = int(L.idkhost_cache_open(os.fsencode(path), key, ctypes.byref(view)))
+    if rc != CACHE_OK:
+        return rc, None
+    try:
+        def get(aid, dtype):
+            es, n = ctypes.c_uint32(), ctypes.c_uint64()
+            p = L.idkhost_cache_array(view, aid, ctypes.byref(es), ctypes.byref(n))
+            if not p or es.value != np.dtype(dtype).itemsize:
+                return None
+            return np.frombuffer((ctypes.c_char * (n.value * es.value)).from_address(p), dtype=dtype).copy() if n.value else np.zeros(0, dtype)
+        nodes, tris, info = get(CACHE_BLAS_NODES, gt.GpuBlasNode), get(CACHE_BLAS_TRIANGLES, gt.GpuBlasTriangle), get(CACHE_BUILD_INFO, np.float64)
+        if nodes is None or tris is None or info is None or len(info) != 3:
+            return CACHE_ERR_FORMAT, None
+        return CACHE_OK, dict(nodes=nodes, triangles=tris, required_stack_size=int(info[0]), fragment_count=int(info[1]), sah=float(info[2]))
+    finally:
+        L.idkhost_cache_close(view)
 
 
 # --------------------------------------------------------------------------- transforms
@@ -181,9 +252,10 @@ class Scene:
         self.source_triangle_count = 0
         self.build_info = []
 
-    def add(self, *models, threads=None):
+    def add(self, *models, threads=None, cache_dir=None):
         """ModelManager.Add (SRC/ModelManager.cs:128-213) + BVH.Add/BlasesBuild (SRC/Bvh/BVH.cs:236-276,300-451):
-        one BLAS + one instance per model."""
+        one BLAS + one instance per model. cache_dir (or $IDKHOST_BVH_CACHE): directory of the on-disk BLAS cache."""
+        cache_dir = cache_dir or os.environ.get("IDKHOST_BVH_CACHE") or None
         for m in models:
             v_off = len(self.positions)
             mesh_off = len(self.meshes)
@@ -215,7 +287,27 @@ class Scene:
             src["MeshId"] = m.tri_mesh + mesh_off
             self.source_triangle_count += len(src)
 
-            b = build_blas(self.positions, src, presplit=not m.refittable, threads=threads)
+            b = None
+            cache_path = None
+            if cache_dir is not None:     # skip the SweepSAH build when this exact model was built before
+                key = blas_source_key(m.positions, m.indices, m.tri_mesh, not m.refittable)
+                cache_path = os.path.join(cache_dir, f"{key:016x}.idkbvh")
+                rc, b = cache_load(cache_path, key) if os.path.exists(cache_path) else (CACHE_ERR_IO, None)
+                if b is not None:         # stored model-relative: rebase onto this scene's vertex / mesh offsets
+                    for f in ("X", "Y", "Z"):
+                        b["triangles"][f] += v_off
+                    b["triangles"]["MeshId"] += mesh_off
+                    b["from_cache"] = True
+            if b is None:
+                b = build_blas(self.positions, src, presplit=not m.refittable, threads=threads)
+                if cache_path is not None:
+                    rel = dict(b)
+                    rel["triangles"] = b["triangles"].copy()
+                    for f in ("X", "Y", "Z"):
+                        rel["triangles"][f] -= v_off
+                    rel["triangles"]["MeshId"] -= mesh_off
+                    os.makedirs(cache_dir, exist_ok=True)
+                    cache_save(cache_path, key, rel)
             desc = np.zeros(1, gt.GpuBlasDesc)
             desc["NodeOffset"] = len(self.blas_nodes)
             desc["NodeCount"] = len(b["nodes"])
@@ -233,7 +325,7 @@ class Scene:
             self.blas_instances = np.concatenate([self.blas_instances, inst])
             self.build_info.append(dict(name=m.name, source_triangles=len(src), fragments=b["fragment_count"],
                                         triangles=len(b["triangles"]), nodes=len(b["nodes"]),
-                                        required_stack_size=b["required_stack_size"], sah=b["sah"]))
+                                        required_stack_size=b["required_stack_size"], sah=b["sah"], from_cache=bool(b.get("from_cache", False))))
         # BVH.UpdateBlasStackSize (BVH.cs:559-567)
         self.blas_stack_size = max(1, int(self.blas_descs["RequiredStackSize"].max())) if len(self.blas_descs) else 1
         return self

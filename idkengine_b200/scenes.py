@@ -279,7 +279,8 @@ def street_canyon(target_tris=3_900_000, seed=SEED + 1, threads=None):
 
 
 # --------------------------------------------------------------------------- multi-BLAS test scene
-def multi_blas(threads=None):
+def multi_blas_models():
+    """room, ball (rotated / scaled instance), crate (refittable: the non-presplit builder path)."""
     specs_room = [dict(color=(0.7, 0.7, 0.7)), dict(color=(1, 1, 1), emissive=(12, 12, 12))]
     meshes, mats = _materials(specs_room)
     a = _Assembler()
@@ -297,7 +298,11 @@ def multi_blas(threads=None):
     c.add(cylinder([0, 0.5, 0], 0.3, 1.0, 24, 6), 0)
     crate = c.model(m3, t3, model_matrix=trs_matrix((1.0, 1.4, 0.7), 45.0, (1.3, 0.7, 0.4)), name="crate")
     crate.refittable = True  # exercises the non-presplit (BLAS.GetUnindexedTriangles) path
-    scene = Scene().add(room, ball, crate, threads=threads)
+    return [room, ball, crate]
+
+
+def multi_blas(threads=None):
+    scene = Scene().add(*multi_blas_models(), threads=threads)
     scene.add_light((-1.0, 2.5, 1.0), (30.0, 28.0, 20.0), 0.3)
     cam = dict(position=(0.0, 1.6, 5.0), view_dir=(0.0, -0.1, -1.0), fov_y_deg=60.0)
     return scene, cam

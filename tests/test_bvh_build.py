@@ -191,3 +191,53 @@ def test_tlas_ploc_structure_and_equivalence(multi_blas):
     tl = ol.trace_rays(sc, rays)
     assert np.array_equal(flat["T"], tl["T"])
     assert np.array_equal(flat["TriangleId"], tl["TriangleId"])
+
+
+# ---- on-disk BLAS cache (include/idkhost_cache.h) ------------------------------------------------------
+def test_blas_cache_round_trip_and_rejects(tmp_path):
+    import time
+    from idkengine_b200 import host, scenes
+    cache = str(tmp_path / "bvh")
+    t0 = time.perf_counter()
+    a, _ = scenes.multi_blas(threads=1)
+    fresh = host.Scene().add(*_models_of_multi_blas(), threads=1, cache_dir=cache)
+    assert not any(i["from_cache"] for i in fresh.build_info)
+    again = host.Scene().add(*_models_of_multi_blas(), threads=1, cache_dir=cache)
+    assert all(i["from_cache"] for i in again.build_info)
+    for f in ("blas_nodes", "blas_triangles", "blas_descs", "positions", "vertices"):
+        assert getattr(fresh, f).tobytes() == getattr(again, f).tobytes() == getattr(a, f).tobytes(), f
+    assert fresh.blas_stack_size == again.blas_stack_size
+    # a different order in the scene rebases the cached triangle ids
+    models = _models_of_multi_blas()
+    swapped = host.Scene().add(models[2], models[0], models[1], threads=1, cache_dir=cache)
+    direct = host.Scene().add(models[2], models[0], models[1], threads=1)
+    assert all(i["from_cache"] for i in swapped.build_info)
+    assert swapped.blas_triangles.tobytes() == direct.blas_triangles.tobytes() and swapped.blas_nodes.tobytes() == direct.blas_nodes.tobytes()
+    # corruption / wrong key / truncation are detected
+    import glob, os
+    files = sorted(glob.glob(os.path.join(cache, "*.idkbvh")))
+    assert len(files) == 3
+    key = int(os.path.basename(files[0]).split(".")[0], 16)
+    assert host.cache_load(files[0], key)[0] == host.CACHE_OK
+    assert host.cache_load(files[0], key ^ 1)[0] == host.CACHE_ERR_KEY
+    raw = bytearray(open(files[0], "rb").read())
+    raw[len(raw) // 2] ^= 0x40
+    bad = str(tmp_path / "bad.idkbvh")
+    open(bad, "wb").write(raw)
+    assert host.cache_load(bad, key)[0] == host.CACHE_ERR_CHECKSUM
+    open(bad, "wb").write(raw[: len(raw) - 64])
+    assert host.cache_load(bad, key)[0] == host.CACHE_ERR_FORMAT
+    open(bad, "wb").write(b"not a cache")
+    assert host.cache_load(bad, key)[0] == host.CACHE_ERR_FORMAT
+    # a corrupt file in the cache directory falls back to a rebuild (and is overwritten)
+    open(files[0], "wb").write(bytes(raw))
+    healed = host.Scene().add(*_models_of_multi_blas(), threads=1, cache_dir=cache)
+    assert sum(i["from_cache"] for i in healed.build_info) == 2
+    assert healed.blas_nodes.tobytes() == a.blas_nodes.tobytes()
+    assert host.cache_load(files[0], key)[0] == host.CACHE_OK
+
+
+def _models_of_multi_blas():
+    """The three models scenes.multi_blas() assembles (room, ball, crate)."""
+    from idkengine_b200 import scenes
+    return scenes.multi_blas_models()

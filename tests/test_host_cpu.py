@@ -32,6 +32,16 @@ def test_library_exports_every_declared_symbol(libidkpt):
     assert libidkpt.idkpt_abi_version() == 2
 
 
+def test_host_library_exports_cache_symbols():
+    from idkengine_b200 import host
+    hdr = open(os.path.join(REPO, "include", "idkhost_cache.h")).read()
+    declared = set(re.findall(r"\b(idkhost_\w+)\s*\(", hdr))
+    assert {"idkhost_hash64", "idkhost_cache_save", "idkhost_cache_open", "idkhost_cache_array", "idkhost_cache_close"} == declared
+    L = host.lib()
+    for name in declared:
+        assert hasattr(L, name), name
+
+
 def test_no_cpu_fallback(libidkpt):
     import torch
     if torch.cuda.is_available():
