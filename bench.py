@@ -221,6 +221,9 @@ def run_ours(args, rank, world, local_rank):
             return out
         pt.EnablePeerGather(rank, world, exchange)
 
+    lanes = int(os.environ.get("IDKPT_LANES", "8"))      # the library default
+    pipelined = lanes > 1 and (world == 1 or peer_gather)      # the NCCL fallback gathers between steps: one sample at a time
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -229,7 +232,11 @@ def run_ours(args, rank, world, local_rank):
     def step(e2e, k=0):
         """e2e: the frame's GpuPerFrameData goes host->device inside Compute(); the finished image of EVERY step is read
         back into pinned host memory (double-buffered, asynchronously, so the transfer overlaps the next step)."""
-        st = pt.Compute()
+        if pipelined:
+            pt.ComputeAsync()         # stats == NULL: queued, up to `lanes` samples in flight
+            st = None
+        else:
+            st = pt.Compute()
         if world == 1:
             if e2e:
                 pt.PresentAsync(pinned[k & 1].data_ptr(), pinned[k & 1].numel() * 4)
@@ -248,6 +255,7 @@ def run_ours(args, rank, world, local_rank):
     def e2e_drain():
         if world == 1 or peer_gather:
             pt.PresentWait()
+            pt.Sync()
         else:
             copy_stream.synchronize()
 
@@ -264,7 +272,8 @@ def run_ours(args, rank, world, local_rank):
         step(True, k)                        # buffer, the copy stream and touches the pinned pages)
     e2e_drain()
 
-    # ---- timed region 1: inputs resident in HBM, no read-back
+    # ---- timed region 1a: inputs resident in HBM, no read-back, ONE sample at a time with per-kernel CUDA events
+    # (the roofline's kernel durations come from here; with pipelining off this is also `value`)
     pt.ResetAccumulation()
     sampler = ClockSampler(local_rank)
     barrier()
@@ -292,6 +301,23 @@ def run_ours(args, rank, world, local_rank):
     wall_ms = (time.perf_counter() - t0) * 1e3
     assert rays == R, "timed region traced a different ray set than the stats replay"
 
+    # ---- timed region 1b: the same K steps queued asynchronously (several samples in flight). Timed on the device with
+    # events on the context's main stream: every sample's FinalDraw runs there in submission order.
+    pipe_ms = None
+    if pipelined:
+        ext = torch.cuda.ExternalStream(pt.StreamHandle(), device=dev)
+        pe0, pe1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        pt.ResetAccumulation()
+        barrier()
+        pe0.record(ext)
+        for _ in range(args.steps):
+            pt.ComputeAsync()
+        pe1.record(ext)
+        pt.Sync()
+        barrier()
+        pipe_ms = pe0.elapsed_time(pe1)
+        assert pt.AccumulatedSamples == args.steps
+
     # ---- timed region 2: end to end through the public API with host buffers (frame H2D, result D2H every step)
     pt.ResetAccumulation()
     barrier()
@@ -310,19 +336,22 @@ def run_ours(args, rank, world, local_rank):
         return float(t.item())
 
     MAX, SUM = (dist.ReduceOp.MAX, dist.ReduceOp.SUM) if world > 1 else (None, None)
-    job_ms = reduce(dev_ms + (0.0 if peer_gather else gather_ms), MAX)        # device time, max over ranks
+    serial_ms = reduce(dev_ms + (0.0 if peer_gather else gather_ms), MAX)     # device time of region 1a, max over ranks
+    job_ms = reduce(pipe_ms, MAX) if pipelined else serial_ms                 # device time of the K timed steps, max over ranks
     # nvidia-smi samples every 100 ms but K steps may last only tens of ms: keep the identical load running (untimed) until
     # the sampler has seen ~0.6 s of it, then stop it. The step count is derived from the reduced time, i.e. equal on all ranks.
     extra_steps = int(min(600, max(0, 600.0 / max(job_ms / args.steps, 1e-3) - args.steps)))
     for k in range(extra_steps):
         step(False)
+    if pipelined:
+        pt.Sync()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
     if clocks is not None:
         clocks["sampled_over"] = f"the {args.steps} timed steps + {extra_steps} identical untimed steps (nvidia-smi -lms 100)"
     per_rank = None
     if world > 1:      # per-rank device times: shows tile imbalance / a slow GPU behind the max-over-ranks figure
-        mine = {"rank": rank, "total": dev_ms / args.steps, "traverse": trav_ms / args.steps, "shade": shade_ms / args.steps,
+        mine = {"rank": rank, "pipelined_total": (pipe_ms / args.steps) if pipelined else None, "total": dev_ms / args.steps, "traverse": trav_ms / args.steps, "shade": shade_ms / args.steps,
                 "gather": gather_ms / args.steps, "rays": rays // args.steps}
         per_rank = [None] * world
         dist.all_gather_object(per_rank, mine)
@@ -341,10 +370,13 @@ def run_ours(args, rank, world, local_rank):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world, scene),
             "rays_per_step": total_rays / args.steps,
+            "serial_ms_per_step": serial_ms / args.steps,
+            "pipeline": (f"{lanes} samples in flight: asynchronous Compute (stats == NULL), per-sample results and accumulation order identical to the "
+                         f"serial path" if pipelined else "off: one sample at a time"),
             "wall_ms_per_step": wall_ms / args.steps,
-            "kernel_ms_per_step": {"traverse": trav_ms / args.steps, "shade": shade_ms / args.steps,
+            "kernel_ms_per_step": {"measured_in": "serial pass (region 1a: one sample in flight, per-kernel CUDA events)", "traverse": trav_ms / args.steps, "shade": shade_ms / args.steps,
                                    "all_gather": gather_ms / args.steps, "total_device": dev_ms / args.steps},
-            "roofline": {"kernel": "k_traverse2 (bounces) + k_traverse (primary rays)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"kernel": "k_traverse2 (bounces) + k_traverse (primary rays)", "measured_in": "serial pass of the same K steps (kernels of different samples overlap in the pipelined pass)", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": measured_traffic(), "traffic_source": "profiles/traffic.json (ncu --set full, heaviest launches)", "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": trav_bytes / max(trav_launches, 1),
                          "launch_ms": trav_ms / max(trav_launches, 1),

@@ -85,7 +85,7 @@ IDKPT_ARRAY_TLAS_NODES, IDKPT_ARRAY_BLAS_NODES, IDKPT_ARRAY_VERTEX_POSITIONS, ID
 EXPORTS = [
     "idkpt_create", "idkpt_destroy", "idkpt_last_error", "idkpt_set_scene", "idkpt_update_range", "idkpt_set_sky",
     "idkpt_resize", "idkpt_reset_accumulation", "idkpt_accumulated_samples", "idkpt_set_accumulated_samples",
-    "idkpt_compute", "idkpt_read_result", "idkpt_write_result", "idkpt_present_async", "idkpt_present_wait",
+    "idkpt_compute", "idkpt_sync", "idkpt_stream_handle", "idkpt_read_result", "idkpt_write_result", "idkpt_present_async", "idkpt_present_wait",
     "idkpt_gather_export", "idkpt_gather_import", "idkpt_gather_device_ptr",
     "idkpt_result_device_ptr", "idkpt_tile_rows",
     "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_trace_rays_any", "idkpt_shadows_ray_traced",
@@ -247,6 +247,10 @@ def load(path=None):
     L.idkpt_post_process.argtypes = [c_vp, P(IdkPtPostSettings), c_i32, c_vp, P(c_f)]
     L.idkpt_ldr_device_ptr.restype = c_i32
     L.idkpt_ldr_device_ptr.argtypes = [c_vp, P(c_vp), P(c_u64)]
+    L.idkpt_stream_handle.restype = c_i32
+    L.idkpt_stream_handle.argtypes = [c_vp, P(c_vp)]
+    L.idkpt_sync.restype = c_i32
+    L.idkpt_sync.argtypes = [c_vp]
     L.idkpt_abi_version.restype = c_u32
     L.idkpt_abi_version.argtypes = []
     if path == _build.LIBIDKPT:

@@ -26,6 +26,22 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
+#define IDK_MAX_LANES 8
+
+struct Lane {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t radianceReady = nullptr;   // recorded on the lane stream after the last shade of a sample
+    cudaEvent_t accDone = nullptr;         // recorded on the main stream after that sample's FinalDraw consumed `radiance`
+    bool accPending = false;
+    bool allocated = false;
+    DevBuf state, aov, alive[2], survivors, keysTmp, sortedAlive, hits, hitXform, debugCost, radiance, aovAlbedoFinal, aovNormalFinal;
+    DevBuf countsDev;              // uint32 counts[IDKPT_MAX_RAY_DEPTH + 1]
+    DevBuf tickets;                // uint32 tickets[2 * (IDKPT_MAX_RAY_DEPTH + 1)] (traverse, compact)
+    DevBuf tileStatus;             // u64 per tile
+    DevBuf keys;                   // ray sorting: key per slot of the compacted alive list
+    IdkSortScratch sortScratch;
+};
+
 struct IdkPtCtx {
     int device = 0;
     int smCount = 148;
@@ -62,22 +78,23 @@ struct IdkPtCtx {
     std::vector<GpuBlasDesc> hostDescs;
     size_t nodeBytes = 0;
 
-    // wavefront buffers
-    DevBuf state, aov, alive[2], survivors, keysTmp, sortedAlive, hits, hitXform, debugCost, radiance, aovAlbedoFinal, aovNormalFinal;
+    // wavefront buffers: one set per lane. A lane is one sample in flight (ray-gen .. last shade) on its own stream; with
+    // several lanes the latency-bound tail bounces of one sample overlap the throughput-bound head of the next
+    // (profiles/r01h_overlap_probe.json). Lane 0 also serves the synchronous path (stats, export, debug).
+    Lane lanes[IDK_MAX_LANES];
+    int laneCount = 8;             // lanes used by asynchronous idkpt_compute (stats == NULL); IDKPT_LANES / CreateInfo.Flags
+    int nextLane = 0;
+    bool asyncPending = false;     // work issued on lane streams / main stream that no host call has waited for yet
     DevBuf images[3];
-    DevBuf countsDev;              // uint32 counts[IDKPT_MAX_RAY_DEPTH + 1]
-    DevBuf tickets;                // uint32 tickets[2 * (IDKPT_MAX_RAY_DEPTH + 1)] (traverse, compact)
-    DevBuf tileStatus;             // u64 per tile
     DevBuf counters;               // TraceCounters
-    DevBuf keys;                   // ray sorting: key per slot of the compacted alive list
     DevBuf countLog;               // per-sample copies of the alive counts (stats only)
-    IdkSortScratch sortScratch;
     uint32_t epoch = 0;
     bool exportEnabled = false;
 
     // launch configuration
     int traverseBlocks = 0, traverseBlocksStats = 0, shadeBlocks = 0, traceRaysBlocks = 0, compactBlocks = 0;
     int traverse1Blocks = 0, traverse1BlocksStats = 0;
+    int traverseBlocksLane = 0, traverse1BlocksLane = 0;   // grids of the asynchronous path: the resident-block budget split between the lanes
     int traverseVariant = 3;       // 1 = k_traverse (one ray per lane, reference loop), 2 = k_traverse2 (phase-scheduled warps),
                                    // 3 = k_traverse for the coherent primary rays, k_traverse2 for every bounce (default)
     TraverseTuning tune = {12, 4};   // swept on B200 (profiles/r01b_tuning.txt)
@@ -187,6 +204,19 @@ static int configure_launches(IdkPtCtx* ctx) {
     ctx->shadeBlocks = std::max(1, n) * ctx->smCount;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_compact, IDK_BLOCK, 0));
     ctx->compactBlocks = std::max(1, std::min(n, 4)) * ctx->smCount;
+    // asynchronous path: `laneCount` samples in flight share the SMs; each lane's persistent traversal grid takes its share of
+    // the resident-block budget (profiles/r01h_overlap_probe.json: 4 x 1 block/SM beats 4 x full grid by 24 % on a 1/8 tile)
+    {
+        const int lanes = std::max(1, ctx->laneCount);
+        const int perSm2 = (ctx->traverseBlocks / ctx->smCount + lanes - 1) / lanes, perSm1 = (ctx->traverse1Blocks / ctx->smCount + lanes - 1) / lanes;
+        ctx->traverseBlocksLane = std::max(1, perSm2) * ctx->smCount;      // profiles/r01h_lanes_probe.json: 3 lanes x 2 blocks/SM, 4+ lanes x 1
+        ctx->traverse1BlocksLane = std::max(1, perSm1) * ctx->smCount;
+    }
+    if (const char* v = getenv("IDKPT_LANE_BLOCKS_PER_SM")) {        // developer knob
+        const int b = std::max(1, atoi(v));
+        ctx->traverseBlocksLane = std::min(ctx->traverseBlocks, b * ctx->smCount);
+        ctx->traverse1BlocksLane = std::min(ctx->traverse1Blocks, b * ctx->smCount);
+    }
     if (const char* v = getenv("IDKPT_TRAVERSE_BLOCKS_PER_SM")) {   // developer knob
         const int b = std::max(1, atoi(v));
         ctx->traverseBlocks = std::min(ctx->traverseBlocks, b * ctx->smCount);
@@ -210,26 +240,94 @@ static int configure_launches(IdkPtCtx* ctx) {
     return IDKPT_OK;
 }
 
+static int allocate_lane(IdkPtCtx* ctx, Lane& ln) {
+    const size_t n = std::max<uint32_t>(ctx->nLocal, 1);
+    CK(ensure(ln.state, n * sizeof(PathState)));
+    CK(ensure(ln.aov, n * 32));
+    for (int i = 0; i < 2; i++) CK(ensure(ln.alive[i], n * 4));
+    CK(ensure(ln.survivors, n * 4));
+    CK(ensure(ln.hits, n * 16));
+    CK(ensure(ln.hitXform, n * 4));
+    CK(ensure(ln.debugCost, n * 4));
+    CK(ensure(ln.radiance, n * 16));
+    CK(ensure(ln.aovAlbedoFinal, n * 16));
+    CK(ensure(ln.aovNormalFinal, n * 16));
+    CK(ensure(ln.countsDev, (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
+    CK(ensure(ln.tickets, 2 * (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
+    CK(ensure(ln.tileStatus, ((n + IDK_BLOCK * IDK_COMPACT_ITEMS - 1) / (IDK_BLOCK * IDK_COMPACT_ITEMS) + 1) * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ln.tileStatus.p, 0, ln.tileStatus.bytes, ctx->stream));
+    if (!ln.stream) CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+    if (!ln.radianceReady) CK(cudaEventCreateWithFlags(&ln.radianceReady, cudaEventDisableTiming));
+    if (!ln.accDone) CK(cudaEventCreateWithFlags(&ln.accDone, cudaEventDisableTiming));
+    CK(cudaStreamSynchronize(ctx->stream));   // the status words are cleared before any lane stream touches them
+    ln.accPending = false;
+    ln.allocated = true;
+    return IDKPT_OK;
+}
+
+static void release_lane(Lane& ln, bool keepStream) {
+    DevBuf* all[] = {&ln.state, &ln.aov, &ln.alive[0], &ln.alive[1], &ln.survivors, &ln.keysTmp, &ln.sortedAlive, &ln.hits, &ln.hitXform, &ln.debugCost,
+                     &ln.radiance, &ln.aovAlbedoFinal, &ln.aovNormalFinal, &ln.countsDev, &ln.tickets, &ln.tileStatus, &ln.keys};
+    for (DevBuf* b : all) release(*b);
+    idk_sort_release(ln.sortScratch);
+    ln.allocated = false;
+    ln.accPending = false;
+    if (!keepStream) {
+        if (ln.stream) { cudaStreamDestroy(ln.stream); ln.stream = nullptr; }
+        if (ln.radianceReady) { cudaEventDestroy(ln.radianceReady); ln.radianceReady = nullptr; }
+        if (ln.accDone) { cudaEventDestroy(ln.accDone); ln.accDone = nullptr; }
+    }
+}
+
+// Wait for everything issued so far: every lane stream and the main (image) stream. Every entry point that reads or
+// changes device data other than idkpt_compute / idkpt_present_async starts with this.
+static cudaError_t drain(IdkPtCtx* ctx) {
+    cudaError_t first = cudaSuccess;
+    for (int i = 0; i < IDK_MAX_LANES; i++)
+        if (ctx->lanes[i].stream) { cudaError_t e = cudaStreamSynchronize(ctx->lanes[i].stream); if (first == cudaSuccess) first = e; }
+    if (ctx->stream) { cudaError_t e = cudaStreamSynchronize(ctx->stream); if (first == cudaSuccess) first = e; }
+    for (int i = 0; i < IDK_MAX_LANES; i++) ctx->lanes[i].accPending = false;
+    ctx->asyncPending = false;
+    return first;
+}
+
+// Errors that only the device knows about (a kernel fault, a peer rank that never delivered its tile) surface at the
+// next host-synchronising call.
+static int check_device_errors(IdkPtCtx* ctx, cudaError_t se, const char* who) {
+    if (se != cudaSuccess) {
+        ctx->lastError = std::string(who) + ": kernel execution failed: " + cudaGetErrorString(se);
+        return IDKPT_ERR_CUDA;
+    }
+    if (ctx->gatherWorld > 1) {
+        uint32_t timedOut = 0;
+        CK(cudaMemcpy(&timedOut, (uint32_t*)ctx->gatherScratch.p + 1, 4, cudaMemcpyDeviceToHost));
+        if (timedOut) {
+            cudaMemset((uint32_t*)ctx->gatherScratch.p + 1, 0, 4);
+            return fail(ctx, IDKPT_ERR_CUDA, "idkpt_compute: timed out waiting for a peer rank's tile (multi-GPU gather)");
+        }
+    }
+    return IDKPT_OK;
+}
+
+// Entry points that change or expose device data wait for the samples in flight first.
+#define DRAIN_PENDING(who)                                                         \
+    do {                                                                           \
+        if (ctx->asyncPending) {                                                   \
+            cudaSetDevice(ctx->device);                                            \
+            int rc_ = check_device_errors(ctx, drain(ctx), who);                   \
+            if (rc_) return rc_;                                                   \
+        }                                                                          \
+    } while (0)
+
 static int allocate_wavefront(IdkPtCtx* ctx) {
     const size_t n = std::max<uint32_t>(ctx->nLocal, 1);
-    CK(ensure(ctx->state, n * sizeof(PathState)));
-    CK(ensure(ctx->aov, n * 32));
-    for (int i = 0; i < 2; i++) CK(ensure(ctx->alive[i], n * 4));
-    CK(ensure(ctx->survivors, n * 4));
-    CK(ensure(ctx->hits, n * 16));
-    CK(ensure(ctx->hitXform, n * 4));
-    CK(ensure(ctx->debugCost, n * 4));
-    CK(ensure(ctx->radiance, n * 16));
-    CK(ensure(ctx->aovAlbedoFinal, n * 16));
-    CK(ensure(ctx->aovNormalFinal, n * 16));
+    for (int i = 1; i < IDK_MAX_LANES; i++) if (ctx->lanes[i].allocated) release_lane(ctx->lanes[i], true);   // re-created on demand at the new size
+    int rc = allocate_lane(ctx, ctx->lanes[0]);
+    if (rc) return rc;
     for (int i = 0; i < 3; i++) {
         CK(ensure(ctx->images[i], n * 16));
         CK(cudaMemsetAsync(ctx->images[i].p, 0, n * 16, ctx->stream));   // Result.Fill(0), PathTracer.cs:305
     }
-    CK(ensure(ctx->countsDev, (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
-    CK(ensure(ctx->tickets, 2 * (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
-    CK(ensure(ctx->tileStatus, ((n + IDK_BLOCK * IDK_COMPACT_ITEMS - 1) / (IDK_BLOCK * IDK_COMPACT_ITEMS) + 1) * sizeof(unsigned long long)));
-    CK(cudaMemsetAsync(ctx->tileStatus.p, 0, ctx->tileStatus.bytes, ctx->stream));
     CK(ensure(ctx->counters, sizeof(TraceCounters)));
     ctx->epoch = 0;
     return IDKPT_OK;
@@ -380,6 +478,8 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
     if (const char* v = getenv("IDKPT_TRAVERSE_VARIANT")) ctx->traverseVariant = std::max(1, std::min(3, atoi(v)));
     if (const char* v = getenv("IDKPT_TUNE_SETUP")) ctx->tune.setupThreshold = std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("IDKPT_TUNE_LEAF")) ctx->tune.leafThreshold = std::max(1, std::min(32, atoi(v)));
+    if (const int fl = (ci->Flags >> 8) & 15) ctx->laneCount = std::min(IDK_MAX_LANES, fl);   // IDKPT_CREATE_LANES(n)
+    if (const char* v = getenv("IDKPT_LANES")) ctx->laneCount = std::max(1, std::min(IDK_MAX_LANES, atoi(v)));
     compute_tile_rows(ctx);
     int rc = allocate_wavefront(ctx);
     if (rc != IDKPT_OK) {
@@ -395,16 +495,14 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
 IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    drain(ctx);
     DevBuf* all[] = {&ctx->nodes, &ctx->triRec, &ctx->blasTris, &ctx->positions, &ctx->descs, &ctx->instances, &ctx->xforms,
-                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->vtxFrame, &ctx->surfRec, &ctx->state, &ctx->aov, &ctx->alive[0],
-                     &ctx->alive[1], &ctx->survivors, &ctx->keysTmp, &ctx->sortedAlive, &ctx->hits, &ctx->hitXform, &ctx->debugCost, &ctx->radiance, &ctx->aovAlbedoFinal,
-                     &ctx->aovNormalFinal, &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->countsDev,
-                     &ctx->tickets, &ctx->tileStatus, &ctx->counters, &ctx->keys, &ctx->countLog, &ctx->skyFaces,
+                     &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->vtxFrame, &ctx->surfRec,
+                     &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->counters, &ctx->countLog, &ctx->skyFaces,
                      &ctx->texPixels, &ctx->texRecs, &ctx->srgbLut, &ctx->bloomDown, &ctx->bloomUp, &ctx->postConsts, &ctx->ldr,
                      &ctx->unskinned, &ctx->joints, &ctx->refitParents, &ctx->refitLocks, &ctx->scratch[0], &ctx->scratch[1], &ctx->scratch[2]};
     for (DevBuf* b : all) release(*b);
-    idk_sort_release(ctx->sortScratch);
+    for (int i = 0; i < IDK_MAX_LANES; i++) release_lane(ctx->lanes[i], false);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
     gather_teardown(ctx);
     if (ctx->copyStream) { cudaStreamSynchronize(ctx->copyStream); cudaStreamDestroy(ctx->copyStream); }
@@ -417,6 +515,7 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
 
 IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     if (!ctx || !s) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: null argument");
+    DRAIN_PENDING("idkpt_set_scene");
     CK(cudaSetDevice(ctx->device));
     if (!s->BlasNodes || !s->BlasTriangles || !s->BlasDescs || !s->BlasInstances || !s->MeshTransforms || !s->Meshes ||
         !s->Materials || !s->Vertices || !s->VertexPositions)
@@ -601,6 +700,7 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
 
 IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t first, uint64_t count, const void* data) {
     if (!ctx || !data) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: null argument");
+    DRAIN_PENDING("idkpt_update_range");
     if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_update_range: no scene");
     CK(cudaSetDevice(ctx->device));
     DevBuf* b = nullptr;
@@ -648,6 +748,7 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
 
 IDKPT_API int idkpt_set_sky(IdkPtCtx* ctx, const IdkPtSkyDesc* sky) {
     if (!ctx || !sky) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_sky: null argument");
+    DRAIN_PENDING("idkpt_set_sky");
     if (sky->FaceSize < 0 || sky->FaceSize > 8192) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_sky: invalid FaceSize");
     CK(cudaSetDevice(ctx->device));
     if (sky->FaceSize > 0) {
@@ -668,6 +769,7 @@ IDKPT_API int idkpt_set_sky(IdkPtCtx* ctx, const IdkPtSkyDesc* sky) {
 
 IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height) {
     if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    DRAIN_PENDING("idkpt_resize");
     if (width <= 0 || height <= 0 || width > 16384 || height > 16384) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_resize: invalid size");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -678,9 +780,11 @@ IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height) {
     compute_tile_rows(ctx);
     int rc = allocate_wavefront(ctx);
     if (rc) return rc;
-    release(ctx->keys);
-    release(ctx->keysTmp);
-    release(ctx->sortedAlive);
+    for (int i = 0; i < IDK_MAX_LANES; i++) {
+        release(ctx->lanes[i].keys);
+        release(ctx->lanes[i].keysTmp);
+        release(ctx->lanes[i].sortedAlive);
+    }
     ctx->accumulatedSamples = 0;
     return IDKPT_OK;
 }
@@ -727,6 +831,18 @@ struct EventPool {
     }
 };
 
+IDKPT_API int idkpt_stream_handle(IdkPtCtx* ctx, void** stream) {
+    if (!ctx || !stream) return IDKPT_ERR_INVALID_ARGUMENT;
+    *stream = (void*)ctx->stream;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_sync(IdkPtCtx* ctx) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    CK(cudaSetDevice(ctx->device));
+    return check_device_errors(ctx, drain(ctx), "idkpt_sync");
+}
+
 IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const IdkPtSettings* st, IdkPtStats* stats) {
     if (!ctx || !frame || !st) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_compute: null argument");
     if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_compute: idkpt_set_scene has not been called");
@@ -740,12 +856,13 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
     const bool wantStats = st->CollectStats != 0 || st->Gpu.DoDebugBVHTraversal != 0;
     const bool sorting = st->DoRaySorting != 0;
     const bool aovs = st->OutputAOVs != 0;
-    if (sorting) {
-        CK(ensure(ctx->keys, (size_t)n * 4));
-        CK(ensure(ctx->keysTmp, (size_t)n * 4));
-        CK(ensure(ctx->sortedAlive, (size_t)n * 4));
-        int rc = idk_sort_prepare(ctx->sortScratch, n);
-        if (rc) return fail(ctx, IDKPT_ERR_OUT_OF_MEMORY, "idkpt_compute: sort scratch allocation failed");
+    // stats == NULL: asynchronous. Samples are issued round-robin onto the lanes and the call returns without waiting
+    // (idkpt_sync, or any call that reads device data, waits). With stats the call is synchronous and runs one sample at
+    // a time on lane 0, exactly the sequence the per-kernel timings describe.
+    const bool async = stats == nullptr && !wantStats && !ctx->exportEnabled && ctx->laneCount > 1;
+    if (!async && ctx->asyncPending) {
+        int rc = check_device_errors(ctx, drain(ctx), "idkpt_compute");
+        if (rc) return rc;
     }
 
     FrameParams f;
@@ -762,10 +879,8 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
 
     EventPool ev{ctx, 0, {}, stats != nullptr};
     const size_t evTotal = ev.begin();
-    uint32_t* counts = (uint32_t*)ctx->countsDev.p;
-    uint32_t* tickets = (uint32_t*)ctx->tickets.p;
     uint32_t launches = 0, traverseLaunches = 0;
-    std::vector<uint32_t> hostCounts((size_t)st->SamplesPerPixel * (IDKPT_MAX_RAY_DEPTH + 1), 0);
+    std::vector<uint32_t> hostCounts(stats ? (size_t)st->SamplesPerPixel * (IDKPT_MAX_RAY_DEPTH + 1) : 0, 0);
     DevBuf& countLog = ctx->countLog;   // per-sample copy of counts for the stats (device-side, read once at the end)
     if (stats) CK(ensure(countLog, hostCounts.size() * sizeof(uint32_t)));
     if (wantStats) CK(cudaMemsetAsync(ctx->counters.p, 0, sizeof(TraceCounters), ctx->stream));
@@ -774,13 +889,30 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
     const int accBlocks = std::min<int>((int)((n + IDK_BLOCK - 1) / IDK_BLOCK), ctx->smCount * 8);
 
     for (int s = 0; s < st->SamplesPerPixel; s++) {
+        Lane& ln = ctx->lanes[async ? ctx->nextLane : 0];
+        if (async) {
+            ctx->nextLane = (ctx->nextLane + 1) % ctx->laneCount;
+            if (!ln.allocated)   // first asynchronous call (or first after a resize): bring up every lane now, not one per call
+                for (int i = 0; i < ctx->laneCount; i++)
+                    if (!ctx->lanes[i].allocated) { int rc = allocate_lane(ctx, ctx->lanes[i]); if (rc) return rc; }
+            if (ln.accPending) CK(cudaStreamWaitEvent(ln.stream, ln.accDone, 0));   // its previous sample's radiance has been consumed
+        }
+        const cudaStream_t ls = async ? ln.stream : ctx->stream;   // the wavefront chain of this sample
+        if (sorting) {
+            CK(ensure(ln.keys, (size_t)n * 4));
+            CK(ensure(ln.keysTmp, (size_t)n * 4));
+            CK(ensure(ln.sortedAlive, (size_t)n * 4));
+            if (idk_sort_prepare(ln.sortScratch, n)) return fail(ctx, IDKPT_ERR_OUT_OF_MEMORY, "idkpt_compute: sort scratch allocation failed");
+        }
+        uint32_t* counts = (uint32_t*)ln.countsDev.p;
+        uint32_t* tickets = (uint32_t*)ln.tickets.p;
         f.accumulatedSamples = ctx->accumulatedSamples;
         // zero the alive counts and work tickets, counts[0] = n (every pixel of the tile traces a primary ray)
-        k_init_sample<<<1, 256, 0, ctx->stream>>>(counts, IDKPT_MAX_RAY_DEPTH + 1, tickets, 2 * (IDKPT_MAX_RAY_DEPTH + 1), n);
+        k_init_sample<<<1, 256, 0, ls>>>(counts, IDKPT_MAX_RAY_DEPTH + 1, tickets, 2 * (IDKPT_MAX_RAY_DEPTH + 1), n);
         launches++;
 
         size_t e0 = ev.begin();
-        k_raygen<<<rgGrid, rgBlock, 0, ctx->stream>>>(f, (PathState*)ctx->state.p);
+        k_raygen<<<rgGrid, rgBlock, 0, ls>>>(f, (PathState*)ln.state.p);
         ev.end(e0, 3);
         launches++;
 
@@ -788,40 +920,41 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             const bool first = j == 0;
             const bool last = j == st->RayDepth - 1;
             // alive list of this bounce: slot -> tile pixel (identity for the first hit)
-            const uint32_t* alive = first ? nullptr : (const uint32_t*)ctx->alive[j & 1].p;
+            const uint32_t* alive = first ? nullptr : (const uint32_t*)ln.alive[j & 1].p;
             if (sorting && j > 1) {
                 // PathTracer.RaySorting(), PathTracer.cs:273-297: stable sort of the alive list by cached key
                 e0 = ev.begin();
-                int nl = idk_sort_by_key(ctx->sortScratch, (const uint32_t*)ctx->keys.p, alive, (uint32_t*)ctx->sortedAlive.p, counts + j, n, ctx->smCount, ctx->stream);
+                int nl = idk_sort_by_key(ln.sortScratch, (const uint32_t*)ln.keys.p, alive, (uint32_t*)ln.sortedAlive.p, counts + j, n, ctx->smCount, ls);
                 ev.end(e0, 2);
                 if (nl < 0) return fail(ctx, IDKPT_ERR_CUDA, "idkpt_compute: sort launch failed");
                 launches += (uint32_t)nl;
-                alive = (const uint32_t*)ctx->sortedAlive.p;
+                alive = (const uint32_t*)ln.sortedAlive.p;
             }
 
             TraverseArgs ta;
             ta.sc = ctx->sc;
-            ta.state = (const PathState*)ctx->state.p;
+            ta.state = (const PathState*)ln.state.p;
             ta.perm = alive;
             ta.count = counts + j;
             ta.ticket = tickets + 2 * j;
-            ta.hits = (HitRec*)ctx->hits.p;
-            ta.hitXform = (uint32_t*)ctx->hitXform.p;
-            ta.debugCost = (float*)ctx->debugCost.p;
+            ta.hits = (HitRec*)ln.hits.p;
+            ta.hitXform = (uint32_t*)ln.hitXform.p;
+            ta.debugCost = (float*)ln.debugCost.p;
             ta.counters = (TraceCounters*)ctx->counters.p;
             ta.traceLights = st->Gpu.DoTraceLights;
             ta.bounce = j;
             e0 = ev.begin();
             if (ctx->traverseVariant == 1 || ctx->sc.useTlas || (ctx->traverseVariant == 3 && first)) {
-                if (wantStats) k_traverse<true><<<ctx->traverse1BlocksStats, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
-                else k_traverse<false><<<ctx->traverse1Blocks, IDK_BLOCK, ctx->stackBytes, ctx->stream>>>(ta);
+                if (wantStats) k_traverse<true><<<ctx->traverse1BlocksStats, IDK_BLOCK, ctx->stackBytes, ls>>>(ta);
+                else k_traverse<false><<<async ? ctx->traverse1BlocksLane : ctx->traverse1Blocks, IDK_BLOCK, ctx->stackBytes, ls>>>(ta);
             } else {
+                const int tb = async ? ctx->traverseBlocksLane : ctx->traverseBlocks;
                 if (ctx->treeletNodes) {
-                    if (wantStats) k_traverse2<true, true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->traverse2Smem, ctx->stream>>>(ta, ctx->tune);
-                    else k_traverse2<false, true><<<ctx->traverseBlocks, IDK_BLOCK, ctx->traverse2Smem, ctx->stream>>>(ta, ctx->tune);
+                    if (wantStats) k_traverse2<true, true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->traverse2Smem, ls>>>(ta, ctx->tune);
+                    else k_traverse2<false, true><<<tb, IDK_BLOCK, ctx->traverse2Smem, ls>>>(ta, ctx->tune);
                 } else {
-                    if (wantStats) k_traverse2<true, false><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->traverse2Smem, ctx->stream>>>(ta, ctx->tune);
-                    else k_traverse2<false, false><<<ctx->traverseBlocks, IDK_BLOCK, ctx->traverse2Smem, ctx->stream>>>(ta, ctx->tune);
+                    if (wantStats) k_traverse2<true, false><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->traverse2Smem, ls>>>(ta, ctx->tune);
+                    else k_traverse2<false, false><<<tb, IDK_BLOCK, ctx->traverse2Smem, ls>>>(ta, ctx->tune);
                 }
             }
             ev.end(e0, 0, j);
@@ -831,43 +964,49 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             ShadeArgs sa;
             sa.sc = ctx->sc;
             sa.f = f;
-            sa.state = (PathState*)ctx->state.p;
-            sa.aov = (float4*)ctx->aov.p;
+            sa.state = (PathState*)ln.state.p;
+            sa.aov = (float4*)ln.aov.p;
             sa.alive = alive;
-            sa.hits = (const HitRec*)ctx->hits.p;
-            sa.hitXform = (const uint32_t*)ctx->hitXform.p;
-            sa.debugCost = (const float*)ctx->debugCost.p;
+            sa.hits = (const HitRec*)ln.hits.p;
+            sa.hitXform = (const uint32_t*)ln.hitXform.p;
+            sa.debugCost = (const float*)ln.debugCost.p;
             sa.count = counts + j;
-            sa.survivors = (uint32_t*)ctx->survivors.p;
-            sa.keysTmp = sorting ? (uint32_t*)ctx->keysTmp.p : nullptr;
-            sa.radiance = (float4*)ctx->radiance.p;
-            sa.aovAlbedoFinal = (float4*)ctx->aovAlbedoFinal.p;
-            sa.aovNormalFinal = (float4*)ctx->aovNormalFinal.p;
+            sa.survivors = (uint32_t*)ln.survivors.p;
+            sa.keysTmp = sorting ? (uint32_t*)ln.keysTmp.p : nullptr;
+            sa.radiance = (float4*)ln.radiance.p;
+            sa.aovAlbedoFinal = (float4*)ln.aovAlbedoFinal.p;
+            sa.aovNormalFinal = (float4*)ln.aovNormalFinal.p;
             sa.exportState = ctx->exportEnabled ? 1 : 0;
             sa.firstHit = first ? 1 : 0;
             sa.lastBounce = last ? 1 : 0;
             sa.outputAovs = aovs ? 1 : 0;
             e0 = ev.begin();
-            if (ctx->sc.textureCount) k_shade<true><<<ctx->shadeBlocks, IDK_BLOCK, 0, ctx->stream>>>(sa);
-            else k_shade<false><<<ctx->shadeBlocks, IDK_BLOCK, 0, ctx->stream>>>(sa);
+            if (ctx->sc.textureCount) k_shade<true><<<ctx->shadeBlocks, IDK_BLOCK, 0, ls>>>(sa);
+            else k_shade<false><<<ctx->shadeBlocks, IDK_BLOCK, 0, ls>>>(sa);
             launches++;
             if (!last) {
                 CompactArgs ca;
-                ca.survivors = (const uint32_t*)ctx->survivors.p;
-                ca.keysTmp = sorting ? (const uint32_t*)ctx->keysTmp.p : nullptr;
+                ca.survivors = (const uint32_t*)ln.survivors.p;
+                ca.keysTmp = sorting ? (const uint32_t*)ln.keysTmp.p : nullptr;
                 ca.count = counts + j;
-                ca.aliveOut = (uint32_t*)ctx->alive[(j + 1) & 1].p;
-                ca.keysOut = sorting ? (uint32_t*)ctx->keys.p : nullptr;
+                ca.aliveOut = (uint32_t*)ln.alive[(j + 1) & 1].p;
+                ca.keysOut = sorting ? (uint32_t*)ln.keys.p : nullptr;
                 ca.countOut = counts + j + 1;
                 ca.ticket = tickets + 2 * j + 1;
-                ca.tileStatus = (unsigned long long*)ctx->tileStatus.p;
+                ca.tileStatus = (unsigned long long*)ln.tileStatus.p;
                 ca.epoch = ++ctx->epoch;
-                k_compact<<<ctx->compactBlocks, IDK_BLOCK, 0, ctx->stream>>>(ca);
+                k_compact<<<ctx->compactBlocks, IDK_BLOCK, 0, ls>>>(ca);
                 launches++;
             }
             ev.end(e0, 1, j);
         }
 
+        // FinalDraw runs on the main (image) stream in issue order: samples accumulate in the order they were submitted
+        // whichever lane finishes first, and presents / read-backs queued on the main stream see a consistent image.
+        if (async) {
+            CK(cudaEventRecord(ln.radianceReady, ls));
+            CK(cudaStreamWaitEvent(ctx->stream, ln.radianceReady, 0));
+        }
         e0 = ev.begin();
         const bool gatherNow = ctx->gatherWorld > 1 && s == st->SamplesPerPixel - 1;
         if (gatherNow) {
@@ -880,20 +1019,22 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             g.doneCounter = (uint32_t*)ctx->gatherScratch.p;
             g.world = ctx->gatherWorld; g.rank = ctx->gatherRank; g.width = ctx->width;
             g.epoch = ++ctx->gatherEpoch;
-            CK(cudaMemsetAsync(ctx->gatherScratch.p, 0, 8, ctx->stream));
-            k_accumulate_scatter<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ctx->radiance.p, (float4*)ctx->images[0].p, n,
+            CK(cudaMemsetAsync(ctx->gatherScratch.p, 0, 4, ctx->stream));
+            k_accumulate_scatter<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ln.radiance.p, (float4*)ctx->images[0].p, n,
                                                                            ctx->accumulatedSamples, st->Gpu.DoDebugBVHTraversal, g);
             if (aovs)   // AOV images stay local to the tile (only Result is gathered)
-                k_accumulate_aov<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ctx->aovAlbedoFinal.p, (const float4*)ctx->aovNormalFinal.p,
+                k_accumulate_aov<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ln.aovAlbedoFinal.p, (const float4*)ln.aovNormalFinal.p,
                                                                            (float4*)ctx->images[1].p, (float4*)ctx->images[2].p, n, ctx->accumulatedSamples);
+            if (async) { CK(cudaEventRecord(ln.accDone, ctx->stream)); ln.accPending = true; }   // before the arrival wait: the lane may go on
             k_gather_wait<<<1, 32, 0, ctx->stream>>>((const uint32_t*)ctx->gatherFlags[b].p, ctx->gatherWorld, g.epoch, (uint32_t*)ctx->gatherScratch.p + 1);
             ctx->gatherCurrent = b;
             launches += aovs ? 3 : 2;
         } else {
-            k_accumulate<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ctx->radiance.p, (const float4*)ctx->aovAlbedoFinal.p,
-                                                                   (const float4*)ctx->aovNormalFinal.p, (float4*)ctx->images[0].p,
+            k_accumulate<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ln.radiance.p, (const float4*)ln.aovAlbedoFinal.p,
+                                                                   (const float4*)ln.aovNormalFinal.p, (float4*)ctx->images[0].p,
                                                                    (float4*)ctx->images[1].p, (float4*)ctx->images[2].p, n,
                                                                    ctx->accumulatedSamples, st->Gpu.DoDebugBVHTraversal, aovs ? 1 : 0);
+            if (async) { CK(cudaEventRecord(ln.accDone, ctx->stream)); ln.accPending = true; }
             launches++;
         }
         ev.end(e0, 3);
@@ -903,16 +1044,13 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
     }
     ev.end(evTotal, 4);
     CK(cudaGetLastError());
-    cudaError_t se = cudaStreamSynchronize(ctx->stream);
-    if (se != cudaSuccess) {
-        ctx->lastError = std::string("idkpt_compute: kernel execution failed: ") + cudaGetErrorString(se);
-        return IDKPT_ERR_CUDA;
+    if (async) {
+        ctx->asyncPending = true;
+        return IDKPT_OK;
     }
-
-    if (ctx->gatherWorld > 1) {
-        uint32_t timedOut = 0;
-        CK(cudaMemcpy(&timedOut, (uint32_t*)ctx->gatherScratch.p + 1, 4, cudaMemcpyDeviceToHost));
-        if (timedOut) return fail(ctx, IDKPT_ERR_CUDA, "idkpt_compute: timed out waiting for a peer rank's tile (multi-GPU gather)");
+    {
+        int rc = check_device_errors(ctx, cudaStreamSynchronize(ctx->stream), "idkpt_compute");
+        if (rc) return rc;
     }
     if (stats) {
         CK(cudaMemcpy(hostCounts.data(), countLog.p, hostCounts.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost));
@@ -980,17 +1118,22 @@ IDKPT_API int idkpt_present_async(IdkPtCtx* ctx, IdkPtImage which, void* dstHost
     if (bytes < (uint64_t)ctx->width * ctx->height * 16) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: buffer smaller than width*height*16");
     CK(cudaSetDevice(ctx->device));
     if ((int)which == 3) {
-        // IDKPT_IMAGE_GATHERED: the full multi-GPU frame. The gather buffers are double-buffered, so the transfer can read
-        // the buffer directly while the next idkpt_compute fills the other one.
+        // IDKPT_IMAGE_GATHERED: the full multi-GPU frame. Snapshot it on the main stream first: with several frames in flight
+        // a peer may start scattering frame k+2 into this buffer as soon as every rank has finished frame k+1, and that is
+        // ordered after this snapshot (main stream: wait(k) -> snapshot(k) -> scatter(k+1)) but not after a slow D2H copy.
         if (ctx->gatherWorld < 2 || ctx->gatherCurrent < 0) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_present_async: no gathered frame yet");
         if (!ctx->copyStream) {
             CK(cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
             CK(cudaEventCreateWithFlags(&ctx->snapDone, cudaEventDisableTiming));
             CK(cudaEventCreateWithFlags(&ctx->copyDone, cudaEventDisableTiming));
         }
+        const size_t full = (size_t)ctx->width * ctx->height * 16;
+        CK(ensure(ctx->presentSnap, full));
+        if (ctx->copyPending) CK(cudaStreamWaitEvent(ctx->stream, ctx->copyDone, 0));   // previous transfer still reads the snapshot
+        CK(cudaMemcpyAsync(ctx->presentSnap.p, ctx->gatherImage[ctx->gatherCurrent].p, full, cudaMemcpyDeviceToDevice, ctx->stream));
         CK(cudaEventRecord(ctx->snapDone, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->copyStream, ctx->snapDone, 0));
-        CK(cudaMemcpyAsync(dstHost, ctx->gatherImage[ctx->gatherCurrent].p, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDeviceToHost, ctx->copyStream));
+        CK(cudaMemcpyAsync(dstHost, ctx->presentSnap.p, full, cudaMemcpyDeviceToHost, ctx->copyStream));
         CK(cudaEventRecord(ctx->copyDone, ctx->copyStream));
         ctx->copyPending = true;
         return IDKPT_OK;
@@ -1035,6 +1178,7 @@ IDKPT_API int idkpt_present_wait(IdkPtCtx* ctx) {
 // image[0], image[1], flags[0], flags[1]). Step 2: exchange the handles (any transport) and import all ranks' handles.
 IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handlesOut, uint64_t bytes) {
     if (!ctx || !handlesOut) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_export: null argument");
+    DRAIN_PENDING("idkpt_gather_export");
     if (bytes < 4 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_export: need 256 bytes");
     CK(cudaSetDevice(ctx->device));
     const size_t imgBytes = (size_t)ctx->width * ctx->height * 16;
@@ -1059,6 +1203,7 @@ IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handlesOut, uint64_t byte
 // allHandles = world x 256 bytes in rank order (this rank's own entry is ignored and replaced by the local pointers).
 IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, const void* allHandles, uint64_t bytes) {
     if (!ctx || !allHandles) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: null argument");
+    DRAIN_PENDING("idkpt_gather_import");
     if (world < 2 || world > IDK_MAX_PEERS || rank < 0 || rank >= world) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: invalid rank / world");
     if (world != ctx->tileCount || rank != ctx->tileIndex) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: rank / world must equal TileIndex / TileCount");
     if (bytes < (uint64_t)world * 4 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: handle buffer too small");
@@ -1087,6 +1232,7 @@ IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, co
 // Full image (all ranks' tiles) of the last idkpt_compute; valid until the compute after next (double-buffered).
 IDKPT_API int idkpt_gather_device_ptr(IdkPtCtx* ctx, void** devPtr, uint64_t* bytes) {
     if (!ctx || !devPtr) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_device_ptr: null argument");
+    DRAIN_PENDING("idkpt_gather_device_ptr");
     if (ctx->gatherWorld < 2 || ctx->gatherCurrent < 0) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_device_ptr: no gathered frame yet");
     *devPtr = ctx->gatherImage[ctx->gatherCurrent].p;
     if (bytes) *bytes = (uint64_t)ctx->width * ctx->height * 16;
@@ -1095,6 +1241,7 @@ IDKPT_API int idkpt_gather_device_ptr(IdkPtCtx* ctx, void** devPtr, uint64_t* by
 
 IDKPT_API int idkpt_result_device_ptr(IdkPtCtx* ctx, IdkPtImage which, void** devPtr, uint64_t* bytes) {
     if (!ctx || !devPtr || (int)which < 0 || (int)which > 2) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_result_device_ptr: invalid argument");
+    DRAIN_PENDING("idkpt_result_device_ptr");
     *devPtr = ctx->images[which].p;
     if (bytes) *bytes = (uint64_t)ctx->nLocal * 16;
     return IDKPT_OK;
@@ -1109,6 +1256,7 @@ IDKPT_API int idkpt_tile_rows(IdkPtCtx* ctx, int32_t* rowCount, int32_t* rowsOut
 
 IDKPT_API int idkpt_read_wavefront_rays(IdkPtCtx* ctx, GpuWavefrontRay* dst, uint64_t count) {
     if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    DRAIN_PENDING("idkpt_read_wavefront_rays");
     if (!dst) {   // dst == NULL arms the export for subsequent idkpt_compute calls (debug / parity feature)
         ctx->exportEnabled = count != 0;
         return IDKPT_OK;
@@ -1117,7 +1265,7 @@ IDKPT_API int idkpt_read_wavefront_rays(IdkPtCtx* ctx, GpuWavefrontRay* dst, uin
     if (count < (uint64_t)ctx->width * ctx->height) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_wavefront_rays: buffer smaller than width*height");
     CK(cudaSetDevice(ctx->device));
     std::vector<PathState> tmp(ctx->nLocal);
-    CK(cudaMemcpyAsync(tmp.data(), ctx->state.p, (size_t)ctx->nLocal * sizeof(PathState), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(tmp.data(), ctx->lanes[0].state.p, (size_t)ctx->nLocal * sizeof(PathState), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     for (size_t i = 0; i < ctx->rows.size(); i++) {
         for (int x = 0; x < ctx->width; x++) {
@@ -1209,6 +1357,7 @@ IDKPT_API int idkpt_post_process(IdkPtCtx* ctx, const IdkPtPostSettings* s, IdkP
 
 IDKPT_API int idkpt_ldr_device_ptr(IdkPtCtx* ctx, void** devPtr, uint64_t* bytes) {
     if (!ctx || !devPtr) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_ldr_device_ptr: null argument");
+    DRAIN_PENDING("idkpt_ldr_device_ptr");
     if (!ctx->ldr.p) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_ldr_device_ptr: call idkpt_post_process first");
     *devPtr = ctx->ldr.p;
     if (bytes) *bytes = (uint64_t)ctx->width * ctx->height * 4;
@@ -1219,6 +1368,7 @@ IDKPT_API int idkpt_ldr_device_ptr(IdkPtCtx* ctx, void** devPtr, uint64_t* bytes
 
 IDKPT_API int idkpt_set_skinning_data(IdkPtCtx* ctx, const GpuUnskinnedVertex* vertices, uint64_t count) {
     if (!ctx || (!vertices && count)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_skinning_data: null argument");
+    DRAIN_PENDING("idkpt_set_skinning_data");
     CK(cudaSetDevice(ctx->device));
     int rc;
     if ((rc = upload(ctx, ctx->unskinned, vertices, count * sizeof(GpuUnskinnedVertex)))) return rc;
@@ -1234,6 +1384,7 @@ IDKPT_API int idkpt_set_skinning_data(IdkPtCtx* ctx, const GpuUnskinnedVertex* v
 
 IDKPT_API int idkpt_skin_vertices(IdkPtCtx* ctx, const float* jointMatrices, uint64_t jointCount, const IdkPtSkinningCmd* cmds, uint32_t cmdCount, float* kernelMs) {
     if (!ctx || (!jointMatrices && jointCount) || (!cmds && cmdCount)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_skin_vertices: null argument");
+    DRAIN_PENDING("idkpt_skin_vertices");
     if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_skin_vertices: no scene");
     if (kernelMs) *kernelMs = 0.0f;
     const uint64_t vtxLimit = std::min(ctx->counts.VertexPositionCount, ctx->counts.VertexCount);
@@ -1271,6 +1422,7 @@ IDKPT_API int idkpt_skin_vertices(IdkPtCtx* ctx, const float* jointMatrices, uin
 
 IDKPT_API int idkpt_blas_refit(IdkPtCtx* ctx, uint32_t first, uint32_t count, float* kernelMs) {
     if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    DRAIN_PENDING("idkpt_blas_refit");
     if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_blas_refit: no scene");
     if ((uint64_t)first + count > ctx->hostDescs.size()) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_blas_refit: BLAS range outside BlasDescs");
     if (ctx->treeletNodes) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_blas_refit: not available with the treelet node layout (IDKPT_TREELET_PAIRS)");

@@ -20,11 +20,11 @@ class IdkPtError(RuntimeError):
 
 
 class PathTracer:
-    def __init__(self, width, height, settings=None, device=0, tile=(8, 0, 1), lib_path=None):
+    def __init__(self, width, height, settings=None, device=0, tile=(8, 0, 1), lib_path=None, lanes=0):
         self._lib = capi.load(lib_path)
         self._ctx = ctypes.c_void_p()
         self._settings = settings or capi.default_settings()
-        ci = capi.IdkPtCreateInfo(device, width, height, tile[0], tile[1], tile[2], 0)
+        ci = capi.IdkPtCreateInfo(device, width, height, tile[0], tile[1], tile[2], (int(lanes) & 15) << 8)   # IDKPT_CREATE_LANES
         rc = self._lib.idkpt_create(ctypes.byref(ci), ctypes.byref(self._ctx))
         if rc != 0:
             msg = self._lib.idkpt_last_error(None)
@@ -131,6 +131,21 @@ class PathTracer:
         self._check(rc, "idkpt_compute")
         self.last_stats = stats
         return stats
+
+    def ComputeAsync(self):
+        """Queue one Compute() without waiting (stats == NULL): several samples stay in flight. Sync() waits."""
+        if self._frame is None:
+            raise IdkPtError("SetFrame() has not been called")
+        self._check(self._lib.idkpt_compute(self._ctx, self._frame.ctypes.data, ctypes.byref(self._settings), None), "idkpt_compute")
+
+    def StreamHandle(self):
+        """cudaStream_t of the main (image) stream, e.g. for torch.cuda.ExternalStream."""
+        h = ctypes.c_void_p()
+        self._check(self._lib.idkpt_stream_handle(self._ctx, ctypes.byref(h)), "idkpt_stream_handle")
+        return h.value
+
+    def Sync(self):
+        self._check(self._lib.idkpt_sync(self._ctx), "idkpt_sync")
 
     def SetSize(self, width, height):
         self._check(self._lib.idkpt_resize(self._ctx, width, height), "idkpt_resize")

@@ -51,6 +51,8 @@ typedef enum IdkPtStatus {
  * Tile fields implement the multi-GPU screen split (one context per GPU):
  * image rows are cut into stripes of TileStripeHeight rows, stripe s belongs to
  * context (s % TileCount) == TileIndex. TileCount <= 1 => the whole image. */
+#define IDKPT_CREATE_LANES(n) (((uint32_t)(n) & 15u) << 8)
+
 typedef struct IdkPtCreateInfo {
     int32_t Device;            /* CUDA device ordinal */
     int32_t Width;
@@ -58,7 +60,7 @@ typedef struct IdkPtCreateInfo {
     int32_t TileStripeHeight;  /* rows per stripe (multiple of 8), 0 => 8 */
     int32_t TileIndex;
     int32_t TileCount;
-    uint32_t Flags;            /* reserved, 0 */
+    uint32_t Flags;            /* 0, or IDKPT_CREATE_LANES(n): samples in flight for asynchronous idkpt_compute (default 8, 1 = off) */
 } IdkPtCreateInfo;
 
 /* Replaces the implicit SSBO bindings 4,5(vertices),8,9..: ModelManager.cs:103-119
@@ -189,8 +191,18 @@ IDKPT_API uint32_t idkpt_accumulated_samples(IdkPtCtx* ctx);                  /*
 IDKPT_API int idkpt_set_accumulated_samples(IdkPtCtx* ctx, uint32_t n);       /* restore a snapshot taken with idkpt_read_result */
 
 /* PathTracer.Compute(), PathTracer.cs:214-271. Images stay on the device.
- * stats may be NULL. Synchronous w.r.t. the returned stats. */
+ * With stats: synchronous, one sample at a time, per-kernel CUDA-event times filled in.
+ * With stats == NULL (and CollectStats / DoDebugBVHTraversal / the wavefront export off): ASYNCHRONOUS. The call queues its
+ * samples and returns; up to `lanes` samples are in flight on separate streams, so the few-ray tail bounces of one sample
+ * overlap the next sample's first bounces. Each sample's values, and the order in which samples are folded into the
+ * images, are exactly those of the synchronous path. idkpt_present_async / idkpt_post_process / idkpt_read_result are
+ * ordered after every queued sample; calls that change the scene or hand out device pointers wait for the queue to
+ * drain; idkpt_sync waits explicitly and reports device-side errors (kernel fault, multi-GPU gather time-out). */
 IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const IdkPtSettings* settings, IdkPtStats* stats);
+IDKPT_API int idkpt_sync(IdkPtCtx* ctx);
+/* The context's main (image) stream as a cudaStream_t: FinalDraw of every sample, presents and post-processing run on it in
+ * submission order, so an event recorded on it after N idkpt_compute calls completes when those N samples are in the image. */
+IDKPT_API int idkpt_stream_handle(IdkPtCtx* ctx, void** stream);
 
 /* Host read-back / restore of an rgba32f image of this context's tile rows in
  * full-image layout (rows not owned by the tile are left untouched). */
