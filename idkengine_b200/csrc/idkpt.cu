@@ -26,7 +26,7 @@ struct DevBuf {
     size_t bytes = 0;
 };
 
-#define IDK_MAX_LANES 8
+#define IDK_MAX_LANES 16
 
 struct Lane {
     cudaStream_t stream = nullptr;
