@@ -83,6 +83,47 @@ __device__ __forceinline__ float det_log2(float x) {
     return (m + y) * 1.44269504f + (float)e;
 }
 
+// One 2-D RGBA8 texture, base level only: compute shaders sample lod 0 (Surface.glsl:57-60).
+struct TexRec {
+    const uchar4* px;
+    int w, h;
+    int wrapS, wrapT;             // GL enums: 10497 REPEAT, 33071 CLAMP_TO_EDGE, 33648 MIRRORED_REPEAT
+    int srgb;                     // rgb decoded through srgbLut before filtering (GL_SRGB8_ALPHA8)
+    int pad;
+};
+
+// ---- material textures: texture(sampler2D, uv) at lod 0 = bilinear on the base level, evaluated explicitly in fp32
+// (same rule as the sky faces / VXGI grid), wrap modes of the glTF sampler (ModelLoader.cs:1166-1196).
+__device__ __forceinline__ int tex_wrap(int i, int n, int mode) {
+    if (mode == 33071) return i < 0 ? 0 : (i > n - 1 ? n - 1 : i);
+    if (mode == 33648) { int m = i % (2 * n); if (m < 0) m += 2 * n; return m < n ? m : 2 * n - 1 - m; }
+    int m = i % n;
+    return m < 0 ? m + n : m;
+}
+__device__ __forceinline__ float4 tex_fetch(const TexRec& t, const float* lut, int x, int y) {
+    const uchar4 c = __ldg(t.px + (size_t)y * t.w + x);
+    if (t.srgb) return make_float4(__ldg(lut + c.x), __ldg(lut + c.y), __ldg(lut + c.z), (float)c.w / 255.0f);
+    return make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+}
+__device__ __forceinline__ float4 tex_lerp(float4 a, float4 b, float t) {
+    const float s = 1.0f - t;
+    return make_float4(a.x * s + b.x * t, a.y * s + b.y * t, a.z * s + b.z * t, a.w * s + b.w * t);
+}
+__device__ __forceinline__ float4 tex_sample_raw(const TexRec* textures, const float* lut, unsigned long long handle, float u, float v) {
+    if (handle == 0) return make_float4(1.0f, 1.0f, 1.0f, 1.0f);
+    const TexRec& t = textures[handle - 1];
+    if (t.wrapS == 10497) u = u - floorf(u);
+    if (t.wrapT == 10497) v = v - floorf(v);
+    const float px = u * (float)t.w - 0.5f, py = v * (float)t.h - 0.5f;
+    const float fx0 = floorf(px), fy0 = floorf(py);
+    const float fx = px - fx0, fy = py - fy0;
+    const int x0 = tex_wrap((int)fx0, t.w, t.wrapS), x1 = tex_wrap((int)fx0 + 1, t.w, t.wrapS);
+    const int y0 = tex_wrap((int)fy0, t.h, t.wrapT), y1 = tex_wrap((int)fy0 + 1, t.h, t.wrapT);
+    const float4 a = tex_lerp(tex_fetch(t, lut, x0, y0), tex_fetch(t, lut, x1, y0), fx);
+    const float4 b = tex_lerp(tex_fetch(t, lut, x0, y1), tex_fetch(t, lut, x1, y1), fx);
+    return tex_lerp(a, b, fy);
+}
+
 // ---- RNG (Random.glsl:16-33)
 __device__ __forceinline__ uint32_t pcg_hash(uint32_t& seed) {
     seed = seed * 747796405u + 2891336453u;

@@ -33,12 +33,15 @@ struct VxScene {
     const GpuMaterial* materials;
     const GpuLight* lights;
     uint32_t lightCount;
+    const TexRec* textures;        // material texture table (idkpt.h IdkPtTextureDesc), handle k = textures[k - 1]
+    const float* srgbLut;
 };
 
 __device__ __forceinline__ float det_tan(float x) { float s, c; det_sincos(x, &s, &c); return s / c; }
 
 struct VxTri {
     f3 P[3], N[3];
+    float U[3], V[3];             // TexCoord of the three vertices
     float qa[3], qb[3];
     float area;
     int a, b;
@@ -63,6 +66,8 @@ __device__ __forceinline__ void vx_setup(const VxScene& sc, const VxGridDev& g, 
         const f3 p = mk3(sc.positions[3 * (size_t)vid[c]], sc.positions[3 * (size_t)vid[c] + 1], sc.positions[3 * (size_t)vid[c] + 2]);
         t.P[c] = xform_point(m0, m1, m2, p);
         t.N[c] = normalize3(xform_normal(i0, i1, i2, decompress_sr11g11b10(sc.vertices[vid[c]].w)));
+        t.U[c] = __uint_as_float(sc.vertices[vid[c]].x);
+        t.V[c] = __uint_as_float(sc.vertices[vid[c]].y);
         uvw[c] = mk3((t.P[c].x - g.gmin[0]) / ex, (t.P[c].y - g.gmin[1]) / ey, (t.P[c].z - g.gmin[2]) / ez);
     }
     const f3 n0 = mk3(uvw[0].x * 2.0f - 1.0f, uvw[0].y * 2.0f - 1.0f, uvw[0].z * 2.0f - 1.0f);
@@ -106,13 +111,23 @@ __device__ __forceinline__ bool vx_pixel(const VxScene& sc, const VxGridDev& g, 
     const int vx = (int)(fu * (float)g.sx[0]), vy = (int)(fv * (float)g.sy[0]), vz = (int)(fw * (float)g.sz[0]);
     if (vx >= g.sx[0] || vy >= g.sy[0] || vz >= g.sz[0]) return false;
 
-    // fragment.glsl:31-79 (constant textures, no point shadows)
+    // fragment.glsl:31-79 (no point shadows). GetSurface(material, TexCoord): the fragment stage samples with implicit
+    // derivatives / mip levels; here the base level is sampled bilinearly like everywhere else in this library.
     const GpuMesh& mesh = sc.meshes[t.meshId];
     const GpuMaterial& mat = sc.materials[mesh.MaterialId];
     const uint32_t c = mat.BaseColorFactor;
-    const f3 albedo = mk3((float)(c & 255u) / 255.0f, (float)((c >> 8) & 255u) / 255.0f, (float)((c >> 16) & 255u) / 255.0f);
-    const float alpha = (float)((c >> 24) & 255u) / 255.0f;
-    const f3 emissive = mk3(mat.EmissiveFactor[0], mat.EmissiveFactor[1], mat.EmissiveFactor[2]) + mesh.EmissiveBias * albedo;
+    f3 albedo = mk3((float)(c & 255u) / 255.0f, (float)((c >> 8) & 255u) / 255.0f, (float)((c >> 16) & 255u) / 255.0f);
+    float alpha = (float)((c >> 24) & 255u) / 255.0f;
+    f3 emissive = mk3(mat.EmissiveFactor[0], mat.EmissiveFactor[1], mat.EmissiveFactor[2]);
+    if ((mat.BaseColorTexture | mat.MetallicRoughnessTexture | mat.NormalTexture | mat.EmissiveTexture | mat.TransmissionTexture) != 0) {
+        const float tu = (t.U[0] * b0 + t.U[1] * b1) + t.U[2] * b2, tv = (t.V[0] * b0 + t.V[1] * b1) + t.V[2] * b2;
+        const float4 base = tex_sample_raw(sc.textures, sc.srgbLut, mat.BaseColorTexture, tu, tv);
+        albedo = mk3(base.x * albedo.x, base.y * albedo.y, base.z * albedo.z);
+        alpha = base.w * alpha;
+        const float4 et = tex_sample_raw(sc.textures, sc.srgbLut, mat.EmissiveTexture, tu, tv);
+        emissive = mk3(et.x * emissive.x, et.y * emissive.y, et.z * emissive.z);
+    }
+    emissive = emissive + mesh.EmissiveBias * albedo;
     f3 direct = mk3(0.0f, 0.0f, 0.0f);
     for (uint32_t l = 0; l < sc.lightCount; l++) {
         const GpuLight& L = sc.lights[l];

@@ -16,6 +16,7 @@
 #include "idk_shadows.cuh"
 #include "idk_dynamic.cuh"
 #include "idk_post.cuh"
+#include "idk_textures_host.h"
 
 #define IDKPT_ABI_VERSION 2u   // 2: IdkPtSceneDesc gained Textures / TextureCount
 
@@ -549,19 +550,10 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     for (uint64_t i = 0; i < s->MeshCount; i++)
         if (s->Meshes[i].MaterialId < 0 || (uint64_t)s->Meshes[i].MaterialId >= s->MaterialCount)
             return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuMesh.MaterialId out of range");
-    if (s->TextureCount && !s->Textures) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: TextureCount without Textures");
-    for (uint64_t i = 0; i < s->TextureCount; i++) {
-        const IdkPtTextureDesc& t = s->Textures[i];
-        if (!t.Pixels || t.Width < 1 || t.Height < 1 || t.Width > 16384 || t.Height > 16384) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: texture without pixels or with an invalid size");
-        if (t.Format != IDKPT_TEX_RGBA8_UNORM && t.Format != IDKPT_TEX_RGBA8_SRGB) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_scene: texture format not supported (RGBA8 unorm / sRGB only; transcode BCn on the host)");
-        for (int k = 0; k < 2; k++) {
-            const int wm = k ? t.WrapT : t.WrapS;
-            if (wm != 10497 && wm != 33071 && wm != 33648) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: texture wrap mode must be REPEAT, CLAMP_TO_EDGE or MIRRORED_REPEAT");
-        }
+    if (const char* terr = idk_validate_textures(s)) {
+        ctx->lastError = std::string("idkpt_set_scene: ") + terr;
+        return strstr(terr, "not supported") ? IDKPT_ERR_UNSUPPORTED : IDKPT_ERR_INVALID_ARGUMENT;
     }
-    for (uint64_t i = 0; i < s->MaterialCount; i++)
-        if (const char* err = validate_material_textures(s->Materials[i], s->TextureCount, "idkpt_set_scene: material texture handle outside the texture table (0 = white, k = Textures[k-1])"))
-            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, err);
 
     int rc;
     // nodes and triangle records share one allocation ("bvh"): [nodes | triRec], so that one L2 access-policy window covers both
@@ -593,8 +585,7 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     if ((rc = upload(ctx, ctx->lights, s->Lights, s->LightCount * sizeof(GpuLight)))) return rc;
     if ((rc = upload(ctx, ctx->tlas, s->TlasNodes, s->UseTlas ? s->TlasNodeCount * sizeof(GpuTlasNode) : 0))) return rc;
     {   // material textures: all base levels in one allocation, 256-byte aligned; records point into it
-        std::vector<size_t> off(s->TextureCount + 1, 0);
-        for (uint64_t i = 0; i < s->TextureCount; i++) off[i + 1] = off[i] + ((((size_t)s->Textures[i].Width * s->Textures[i].Height * 4) + 255) & ~(size_t)255);
+        const std::vector<size_t> off = idk_texture_offsets(s);
         CK(ensure(ctx->texPixels, std::max<size_t>(off[s->TextureCount], 16)));
         std::vector<TexRec> recs(s->TextureCount);
         for (uint64_t i = 0; i < s->TextureCount; i++) {
@@ -605,11 +596,8 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
             recs[i].srgb = t.Format == IDKPT_TEX_RGBA8_SRGB ? 1 : 0; recs[i].pad = 0;
         }
         if ((rc = upload(ctx, ctx->texRecs, recs.data(), recs.size() * sizeof(TexRec)))) return rc;
-        float lut[256];   // GL_SRGB8 decode (OpenGL 4.6 spec 8.24), evaluated in double and rounded once
-        for (int i = 0; i < 256; i++) {
-            const double cs = i / 255.0;
-            lut[i] = (float)(cs <= 0.04045 ? cs / 12.92 : pow((cs + 0.055) / 1.055, 2.4));
-        }
+        float lut[256];
+        idk_srgb_lut(lut);
         if ((rc = upload(ctx, ctx->srgbLut, lut, sizeof(lut)))) return rc;
         CK(cudaStreamSynchronize(ctx->stream));   // recs / lut are locals
     }

@@ -10,6 +10,7 @@
 
 #include "../../include/idkvx.h"
 #include "idk_vxgi.cuh"
+#include "idk_textures_host.h"
 
 static thread_local std::string g_vxCreateError;
 
@@ -27,6 +28,7 @@ struct IdkVxCtx {
     std::vector<GpuBlasInstance> hostInstances;
     void* dPositions = nullptr; void* dVertices = nullptr; void* dTris = nullptr; void* dDescs = nullptr; void* dInstances = nullptr;
     void* dXforms = nullptr; void* dMeshes = nullptr; void* dMaterials = nullptr; void* dLights = nullptr;
+    void* dTexPixels = nullptr; void* dTexRecs = nullptr; void* dSrgbLut = nullptr;
     void* dQueue = nullptr; void* dQueueCount = nullptr; void* dCounters = nullptr;
     size_t queueCapacity = 0;
 };
@@ -116,7 +118,7 @@ IDKPT_API void idkvx_destroy(IdkVxCtx* ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
     void* all[] = {ctx->gridMem, ctx->dPositions, ctx->dVertices, ctx->dTris, ctx->dDescs, ctx->dInstances, ctx->dXforms, ctx->dMeshes,
-                   ctx->dMaterials, ctx->dLights, ctx->dQueue, ctx->dQueueCount, ctx->dCounters};
+                   ctx->dMaterials, ctx->dLights, ctx->dTexPixels, ctx->dTexRecs, ctx->dSrgbLut, ctx->dQueue, ctx->dQueueCount, ctx->dCounters};
     for (void* p : all) if (p) cudaFree(p);
     cudaStreamDestroy(ctx->stream);
     delete ctx;
@@ -155,10 +157,9 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
     for (uint64_t i = 0; i < s->MeshCount; i++)
         if (s->Meshes[i].MaterialId < 0 || (uint64_t)s->Meshes[i].MaterialId >= s->MaterialCount)
             return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_set_scene: GpuMesh.MaterialId out of range");
-    for (uint64_t i = 0; i < s->MaterialCount; i++) {
-        const GpuMaterial& m = s->Materials[i];
-        if (m.BaseColorTexture || m.MetallicRoughnessTexture || m.NormalTexture || m.EmissiveTexture || m.TransmissionTexture)
-            return vfail(ctx, IDKPT_ERR_UNSUPPORTED, "idkvx_set_scene: the voxeliser takes factor-only materials (texture handles must be 0)");
+    if (const char* terr = idk_validate_textures(s)) {
+        ctx->lastError = std::string("idkvx_set_scene: ") + terr;
+        return strstr(terr, "not supported") ? IDKPT_ERR_UNSUPPORTED : IDKPT_ERR_INVALID_ARGUMENT;
     }
     int rc;
     if ((rc = vupload(ctx, &ctx->dPositions, s->VertexPositions, s->VertexPositionCount * sizeof(PackedVec3)))) return rc;
@@ -170,6 +171,24 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
     if ((rc = vupload(ctx, &ctx->dMeshes, s->Meshes, s->MeshCount * sizeof(GpuMesh)))) return rc;
     if ((rc = vupload(ctx, &ctx->dMaterials, s->Materials, s->MaterialCount * sizeof(GpuMaterial)))) return rc;
     if ((rc = vupload(ctx, &ctx->dLights, s->Lights, s->LightCount * sizeof(GpuLight)))) return rc;
+    {   // material textures (BaseColor / Emissive are the slots the voxeliser's fragment stage uses)
+        const std::vector<size_t> off = idk_texture_offsets(s);
+        std::vector<unsigned char> packed(std::max<size_t>(off[s->TextureCount], 16), 0);
+        std::vector<TexRec> recs(std::max<uint64_t>(s->TextureCount, 1));
+        for (uint64_t i = 0; i < s->TextureCount; i++) memcpy(packed.data() + off[i], s->Textures[i].Pixels, (size_t)s->Textures[i].Width * s->Textures[i].Height * 4);
+        if ((rc = vupload(ctx, &ctx->dTexPixels, packed.data(), packed.size()))) return rc;
+        for (uint64_t i = 0; i < s->TextureCount; i++) {
+            const IdkPtTextureDesc& t = s->Textures[i];
+            recs[i].px = (const uchar4*)((const char*)ctx->dTexPixels + off[i]);
+            recs[i].w = t.Width; recs[i].h = t.Height; recs[i].wrapS = t.WrapS; recs[i].wrapT = t.WrapT;
+            recs[i].srgb = t.Format == IDKPT_TEX_RGBA8_SRGB ? 1 : 0; recs[i].pad = 0;
+        }
+        if ((rc = vupload(ctx, &ctx->dTexRecs, recs.data(), recs.size() * sizeof(TexRec)))) return rc;
+        float lut[256];
+        idk_srgb_lut(lut);
+        if ((rc = vupload(ctx, &ctx->dSrgbLut, lut, sizeof(lut)))) return rc;
+        VCK(cudaStreamSynchronize(ctx->stream));   // packed / recs / lut are locals
+    }
     size_t maxTris = 0;
     ctx->hostDescs.assign(s->BlasDescs, s->BlasDescs + s->BlasDescCount);
     ctx->hostInstances.assign(s->BlasInstances, s->BlasInstances + s->BlasInstanceCount);
@@ -187,6 +206,8 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
     sc.meshes = (const GpuMesh*)ctx->dMeshes;
     sc.materials = (const GpuMaterial*)ctx->dMaterials;
     sc.lights = (const GpuLight*)ctx->dLights;
+    sc.textures = (const TexRec*)ctx->dTexRecs;
+    sc.srgbLut = (const float*)ctx->dSrgbLut;
     sc.lightCount = (uint32_t)s->LightCount;
     ctx->counts = *s;
     VCK(cudaStreamSynchronize(ctx->stream));

@@ -113,3 +113,40 @@ def test_gpu_vxgi_errors():
         scene.lights["PointShadowIndex"][0] = 0
         with pytest.raises(vxgi.IdkVxError, match="point-shadowed"):
             vx.SetScene(scene)
+
+
+# ---- material textures in the voxeliser (BaseColor / Emissive slots, base level, same sampler rules as the path tracer)
+TEX_GRID_MIN, TEX_GRID_MAX = (-3.1, -0.1, -3.1), (3.1, 4.1, 3.1)
+
+
+def test_oracle_voxelize_textured_differs_from_factor_only():
+    import copy
+    scene, cam = scenes.textured_room(threads=1)
+    ci = vxgi.create_info(40, TEX_GRID_MIN, TEX_GRID_MAX)
+    levels, raw, frags = ol.vx_voxelize(scene, ci)
+    plain = copy.deepcopy(scene)
+    for f in ("BaseColorTexture", "MetallicRoughnessTexture", "NormalTexture", "EmissiveTexture", "TransmissionTexture"):
+        plain.materials[f] = 0
+    levels_p, _, frags_p = ol.vx_voxelize(plain, ci)
+    assert frags == frags_p                                   # same coverage
+    a, b = levels[0].astype(np.float32), levels_p[0].astype(np.float32)
+    assert np.array_equal(a[..., 3], b[..., 3])               # same written voxels
+    assert not np.array_equal(a[..., :3], b[..., :3])         # different colours
+    assert (a[..., :3] <= b[..., :3] + 1e-3).all()            # textures only darken the factor-only albedo / emission here
+
+
+@pytest.mark.gpu
+def test_gpu_voxelize_textured_matches_oracle():
+    scene, cam = scenes.textured_room(threads=1)
+    ci = vxgi.create_info((48, 40, 56), TEX_GRID_MIN, TEX_GRID_MAX)
+    levels, raw, frags = ol.vx_voxelize(scene, ci)
+    with vxgi.Voxelizer((48, 40, 56), TEX_GRID_MIN, TEX_GRID_MAX) as vx:
+        vx.SetScene(scene)
+        s = vx.Render()
+        assert s.Fragments == frags
+        for l, lv in enumerate(levels):
+            assert np.array_equal(vx.ReadLevel(l).view(np.uint16), lv.view(np.uint16)), f"level {l}"
+        bad = scenes.textured_room(threads=1)[0]
+        bad.materials["EmissiveTexture"][0] = 77
+        with pytest.raises(vxgi.IdkVxError, match="texture"):
+            vx.SetScene(bad)
