@@ -83,7 +83,7 @@ IDKPT_ARRAY_TLAS_NODES, IDKPT_ARRAY_BLAS_NODES, IDKPT_ARRAY_VERTEX_POSITIONS, ID
 
 # every symbol include/idkpt.h declares
 EXPORTS = [
-    "idkpt_create", "idkpt_destroy", "idkpt_last_error", "idkpt_set_scene", "idkpt_update_range", "idkpt_set_sky",
+    "idkpt_create", "idkpt_destroy", "idkpt_last_error", "idkpt_set_scene", "idkpt_update_range", "idkpt_set_sky", "idkpt_set_textures",
     "idkpt_resize", "idkpt_reset_accumulation", "idkpt_accumulated_samples", "idkpt_set_accumulated_samples",
     "idkpt_compute", "idkpt_sync", "idkpt_stream_handle", "idkpt_read_result", "idkpt_write_result", "idkpt_present_async", "idkpt_present_wait",
     "idkpt_gather_export", "idkpt_gather_import", "idkpt_gather_device_ptr",
@@ -145,15 +145,23 @@ def scene_desc(scene):
     d.BlasStackSize = int(scene.blas_stack_size)
     textures = getattr(scene, "textures", [])
     if textures:
-        arr = (IdkPtTextureDesc * len(textures))()
-        for i, t in enumerate(textures):
-            px = np.ascontiguousarray(t["pixels"], np.uint8)
-            keep.append(px)
-            arr[i] = IdkPtTextureDesc(px.ctypes.data, px.shape[1], px.shape[0], IDKPT_TEX_RGBA8_SRGB if t.get("srgb") else IDKPT_TEX_RGBA8_UNORM,
-                                      t.get("wrap_s", GL_REPEAT), t.get("wrap_t", GL_REPEAT), 0)
-        keep.append(arr)
+        arr, tkeep = texture_descs(textures)
+        keep.extend(tkeep)
         d.Textures, d.TextureCount = ctypes.addressof(arr), len(textures)
     return d, keep
+
+
+def texture_descs(textures):
+    """IdkPtTextureDesc array for a list of dict(pixels [H, W, 4] uint8, srgb, wrap_s, wrap_t). Returns (array, keepalive)."""
+    keep = []
+    arr = (IdkPtTextureDesc * max(len(textures), 1))()
+    for i, t in enumerate(textures):
+        px = np.ascontiguousarray(t["pixels"], np.uint8)
+        keep.append(px)
+        arr[i] = IdkPtTextureDesc(px.ctypes.data, px.shape[1], px.shape[0], IDKPT_TEX_RGBA8_SRGB if t.get("srgb") else IDKPT_TEX_RGBA8_UNORM,
+                                  t.get("wrap_s", GL_REPEAT), t.get("wrap_t", GL_REPEAT), 0)
+    keep.append(arr)
+    return arr, keep
 
 
 def sky_desc(color=(0.6, 0.7, 0.9), faces=None):
@@ -249,6 +257,8 @@ def load(path=None):
     L.idkpt_ldr_device_ptr.argtypes = [c_vp, P(c_vp), P(c_u64)]
     L.idkpt_stream_handle.restype = c_i32
     L.idkpt_stream_handle.argtypes = [c_vp, P(c_vp)]
+    L.idkpt_set_textures.restype = c_i32
+    L.idkpt_set_textures.argtypes = [c_vp, c_vp, c_u64]
     L.idkpt_sync.restype = c_i32
     L.idkpt_sync.argtypes = [c_vp]
     L.idkpt_abi_version.restype = c_u32

@@ -65,6 +65,7 @@ struct IdkPtCtx {
     DevBuf skyFaces;
     int skyFaceSize = 0;
     DevBuf texPixels, texRecs, srgbLut;   // material textures (RGBA8 base levels), their records, sRGB decode table
+    std::vector<uint64_t> hostMaterialMaxHandle;   // per material: largest texture handle it uses (validation of later edits)
 
     // host-array entry points (trace_rays, shadows): device staging buffers, kept between calls
     DevBuf scratch[3];
@@ -390,6 +391,36 @@ static const char* validate_material_textures(const GpuMaterial& m, uint64_t tex
     return nullptr;
 }
 
+static uint64_t material_max_handle(const GpuMaterial& m) {
+    return std::max(std::max(std::max(m.BaseColorTexture, m.MetallicRoughnessTexture), std::max(m.NormalTexture, m.EmissiveTexture)), m.TransmissionTexture);
+}
+
+// Material textures: all base levels in one allocation, 256-byte aligned; 32-byte records point into it.
+static int upload_textures(IdkPtCtx* ctx, const IdkPtTextureDesc* textures, uint64_t count) {
+    IdkPtSceneDesc tmp = {};
+    tmp.Textures = textures; tmp.TextureCount = count;
+    const std::vector<size_t> off = idk_texture_offsets(&tmp);
+    CK(ensure(ctx->texPixels, std::max<size_t>(off[count], 16)));
+    std::vector<TexRec> recs(count);
+    for (uint64_t i = 0; i < count; i++) {
+        const IdkPtTextureDesc& t = textures[i];
+        CK(cudaMemcpyAsync((char*)ctx->texPixels.p + off[i], t.Pixels, (size_t)t.Width * t.Height * 4, cudaMemcpyHostToDevice, ctx->stream));
+        recs[i].px = (const uchar4*)((char*)ctx->texPixels.p + off[i]);
+        recs[i].w = t.Width; recs[i].h = t.Height; recs[i].wrapS = t.WrapS; recs[i].wrapT = t.WrapT;
+        recs[i].srgb = t.Format == IDKPT_TEX_RGBA8_SRGB ? 1 : 0; recs[i].pad = 0;
+    }
+    int rc;
+    if ((rc = upload(ctx, ctx->texRecs, recs.data(), recs.size() * sizeof(TexRec)))) return rc;
+    float lut[256];
+    idk_srgb_lut(lut);
+    if ((rc = upload(ctx, ctx->srgbLut, lut, sizeof(lut)))) return rc;
+    CK(cudaStreamSynchronize(ctx->stream));   // recs / lut are locals
+    ctx->sc.textures = (const TexRec*)ctx->texRecs.p;
+    ctx->sc.textureCount = (uint32_t)count;
+    ctx->sc.srgbLut = (const float*)ctx->srgbLut.p;
+    return IDKPT_OK;
+}
+
 static const char* validate_blas(const GpuBlasNode* nodes, const GpuBlasDesc& d, int blasStackSize) {
     const int n = d.NodeCount;
     if (n < 4 || (n & 1)) return "idkpt_set_scene: BLAS node count must be even and >= 4";
@@ -584,23 +615,9 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     if ((rc = upload(ctx, ctx->vertices, s->Vertices, s->VertexCount * sizeof(GpuVertex)))) return rc;
     if ((rc = upload(ctx, ctx->lights, s->Lights, s->LightCount * sizeof(GpuLight)))) return rc;
     if ((rc = upload(ctx, ctx->tlas, s->TlasNodes, s->UseTlas ? s->TlasNodeCount * sizeof(GpuTlasNode) : 0))) return rc;
-    {   // material textures: all base levels in one allocation, 256-byte aligned; records point into it
-        const std::vector<size_t> off = idk_texture_offsets(s);
-        CK(ensure(ctx->texPixels, std::max<size_t>(off[s->TextureCount], 16)));
-        std::vector<TexRec> recs(s->TextureCount);
-        for (uint64_t i = 0; i < s->TextureCount; i++) {
-            const IdkPtTextureDesc& t = s->Textures[i];
-            CK(cudaMemcpyAsync((char*)ctx->texPixels.p + off[i], t.Pixels, (size_t)t.Width * t.Height * 4, cudaMemcpyHostToDevice, ctx->stream));
-            recs[i].px = (const uchar4*)((char*)ctx->texPixels.p + off[i]);
-            recs[i].w = t.Width; recs[i].h = t.Height; recs[i].wrapS = t.WrapS; recs[i].wrapT = t.WrapT;
-            recs[i].srgb = t.Format == IDKPT_TEX_RGBA8_SRGB ? 1 : 0; recs[i].pad = 0;
-        }
-        if ((rc = upload(ctx, ctx->texRecs, recs.data(), recs.size() * sizeof(TexRec)))) return rc;
-        float lut[256];
-        idk_srgb_lut(lut);
-        if ((rc = upload(ctx, ctx->srgbLut, lut, sizeof(lut)))) return rc;
-        CK(cudaStreamSynchronize(ctx->stream));   // recs / lut are locals
-    }
+    if ((rc = upload_textures(ctx, s->Textures, s->TextureCount))) return rc;
+    ctx->hostMaterialMaxHandle.assign(s->MaterialCount, 0);
+    for (uint64_t i = 0; i < s->MaterialCount; i++) ctx->hostMaterialMaxHandle[i] = material_max_handle(s->Materials[i]);
 
     // triangle vertex ids must index the position / vertex arrays
     // (checked on the host copy: cheap relative to the BVH build that produced it)
@@ -722,6 +739,7 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
         for (uint64_t i = 0; i < count; i++)
             if (const char* err = validate_material_textures(m[i], ctx->counts.TextureCount, "idkpt_update_range: material texture handle outside the texture table"))
                 return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, err);
+        for (uint64_t i = 0; i < count; i++) ctx->hostMaterialMaxHandle[first + i] = material_max_handle(m[i]);
     }
     CK(cudaMemcpyAsync((char*)b->p + first * elem, data, count * elem, cudaMemcpyHostToDevice, ctx->stream));
     if ((which == IDKPT_ARRAY_MESHES || which == IDKPT_ARRAY_MATERIALS) && ctx->counts.MeshCount) {
@@ -751,6 +769,29 @@ IDKPT_API int idkpt_set_sky(IdkPtCtx* ctx, const IdkPtSkyDesc* sky) {
     ctx->sc.skyR = ctx->sky[0]; ctx->sc.skyG = ctx->sky[1]; ctx->sc.skyB = ctx->sky[2];
     ctx->sc.skyFaces = ctx->skyFaceSize ? (const float4*)ctx->skyFaces.p : nullptr;
     ctx->sc.skyFaceSize = ctx->skyFaceSize;
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+// Replaces the texture table (SURVEY 8b idkpt_set_textures): e.g. streamed-in higher-resolution images. Handles already
+// stored in the materials must stay valid.
+IDKPT_API int idkpt_set_textures(IdkPtCtx* ctx, const IdkPtTextureDesc* textures, uint64_t count) {
+    if (!ctx || (!textures && count)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_textures: null argument");
+    DRAIN_PENDING("idkpt_set_textures");
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_set_textures: no scene");
+    IdkPtSceneDesc tmp = {};
+    tmp.Textures = textures; tmp.TextureCount = count;
+    if (const char* terr = idk_validate_textures(&tmp)) {
+        ctx->lastError = std::string("idkpt_set_textures: ") + terr;
+        return strstr(terr, "not supported") ? IDKPT_ERR_UNSUPPORTED : IDKPT_ERR_INVALID_ARGUMENT;
+    }
+    for (uint64_t h : ctx->hostMaterialMaxHandle)
+        if (h > count) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_textures: a material references a texture beyond the new table");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int rc = upload_textures(ctx, textures, count);
+    if (rc) return rc;
+    ctx->counts.TextureCount = count;
     ctx->accumulatedSamples = 0;
     return IDKPT_OK;
 }

@@ -107,6 +107,11 @@ class PathTracer:
         self._check(self._lib.idkpt_blas_refit(self._ctx, first, count, ctypes.byref(ms)), "idkpt_blas_refit")
         return ms.value
 
+    def SetTextures(self, textures):
+        """Replace the material texture table (list of dict(pixels, srgb, wrap_s, wrap_t), as host.Scene.textures)."""
+        arr, keep = capi.texture_descs(textures)
+        self._check(self._lib.idkpt_set_textures(self._ctx, ctypes.addressof(arr) if textures else None, len(textures)), "idkpt_set_textures")
+
     def SetSky(self, color, faces=None):
         """Constant colour, or cubemap faces [6, N, N, 4] float32 (SkyBoxManager's samplerCube, UBO 5)."""
         s = capi.sky_desc(color, faces)

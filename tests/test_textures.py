@@ -133,3 +133,30 @@ def test_texture_handle_validation(textured):
         ok = good.materials[:1].copy()
         ok["BaseColorTexture"] = 2
         pt.UpdateRange(capi.IDKPT_ARRAY_MATERIALS, 0, ok)
+
+
+@pytest.mark.gpu
+def test_set_textures_replaces_the_table(textured):
+    from idkengine_b200.pathtracer import PathTracer
+    scene = copy.deepcopy(textured[0])
+    cam = textured[1]
+    w, h = 128, 96
+    frame = scenes.camera_frame(cam, w, h)
+    s = capi.default_settings()
+    swapped = copy.deepcopy(scene)
+    for t in swapped.textures:
+        t["pixels"] = np.ascontiguousarray(255 - t["pixels"][::-1, :, :])
+        t["pixels"][..., 3] = 255
+    with PathTracer(w, h, s) as pt:
+        pt.SetScene(scene); pt.SetSky((0.6, 0.7, 0.9)); pt.SetFrame(frame)
+        pt.Compute()
+        before = pt.Result.copy()
+        pt.SetTextures(swapped.textures)
+        assert pt.AccumulatedSamples == 0
+        pt.Compute()
+        after = pt.Result.copy()
+        with pytest.raises(RuntimeError, match="beyond the new table"):
+            pt.SetTextures(swapped.textures[:3])
+    o = ol.path_trace(swapped, frame, s, w, h)
+    assert np.array_equal(after.view(np.uint32), o.result.view(np.uint32))
+    assert not np.array_equal(before, after)
