@@ -42,6 +42,13 @@ def test_host_library_exports_cache_symbols():
         assert hasattr(L, name), name
 
 
+def test_integration_doc_names_every_entry_point():
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    vx = set(re.findall(r"\b(idkvx_\w+)\s*\(", open(os.path.join(REPO, "include", "idkvx.h")).read()))
+    missing = [n for n in list(capi.EXPORTS) + sorted(vx) if n not in doc]
+    assert not missing, missing
+
+
 def test_no_cpu_fallback(libidkpt):
     import torch
     if torch.cuda.is_available():
