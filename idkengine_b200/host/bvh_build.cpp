@@ -26,7 +26,10 @@
 #include <vector>
 #include <algorithm>
 #include <thread>
+#include <chrono>
 #include <atomic>
+#include <mutex>
+#include <condition_variable>
 #include <string>
 
 #include "../../include/idk_gpu_types.h"
@@ -378,6 +381,110 @@ static ObjectSplit trySplit(const GpuBlasNode& parent, BuildData& bd, const Sett
     return best;
 }
 
+
+// ---- wide variant of TrySplit for the few huge nodes at the top of the tree --------------------------------------------------
+// Same decisions as trySplit, bit for bit: the six box scans (prefix = left cost, suffix = right cost, per axis) are
+// computed in full by up to six threads (min/max accumulation is exact, so a scan computed in full equals the
+// reference's early-terminated one wherever the reference looks at it); the reference's sweep loop with its early-outs
+// then runs over the precomputed costs. The two child boxes and the three stable partitions run concurrently as well.
+struct WideScratch {
+    std::vector<float> L[3], R[3];   // indexed by absolute fragment position
+    void ensure(int n) { for (int a = 0; a < 3; a++) { if ((int)L[a].size() < n) { L[a].resize(n); R[a].resize(n); } } }
+};
+
+template <class F>
+static void runTasks(int taskCount, int threads, F&& f) {
+    const int workers = std::max(1, std::min(threads, taskCount));
+    if (workers == 1) { for (int t = 0; t < taskCount; t++) f(t); return; }
+    std::atomic<int> next(0);
+    std::vector<std::thread> pool;
+    for (int w = 0; w < workers - 1; w++) pool.emplace_back([&]() { for (;;) { int t = next.fetch_add(1); if (t >= taskCount) break; f(t); } });
+    for (;;) { int t = next.fetch_add(1); if (t >= taskCount) break; f(t); }
+    for (auto& th : pool) th.join();
+}
+
+static ObjectSplit trySplitWide(const GpuBlasNode& parent, BuildData& bd, const Settings& s, WideScratch& ws) {
+    ObjectSplit none = {0, 0, 0.0f, false};
+    Box parentBox = {{parent.Min[0], parent.Min[1], parent.Min[2]}, {parent.Max[0], parent.Max[1], parent.Max[2]}};
+    if (parent.TriCount <= s.stopSplittingThreshold) return none;
+    const int start = parent.TriStartOrChild;
+    const int end = parent.TriStartOrChild + parent.TriCount;
+    const Box* fragBounds = bd.frags.bounds.data();
+    ws.ensure(bd.n());
+
+    runTasks(6, s.threads, [&](int task) {
+        const int axis = task >> 1;
+        const int* ids = bd.sorted[axis].data();
+        if (task & 1) {           // suffix: R[i] = halfArea(box of [i, end)) * (end - i)
+            Box acc = Box::empty();
+            float counter = 0.0f;
+            float* R = ws.R[axis].data();
+            for (int i = end - 1; i >= start + 1; i--) { counter++; acc.grow(fragBounds[ids[i]]); R[i] = acc.halfArea() * counter; }
+        } else {                  // prefix: L[i] = halfArea(box of [start, i]) * (i - start + 1)
+            Box acc = Box::empty();
+            float counter = 0.0f;
+            float* L = ws.L[axis].data();
+            for (int i = start; i < end - 1; i++) { counter++; acc.grow(fragBounds[ids[i]]); L[i] = acc.halfArea() * counter; }
+        }
+    });
+
+    ObjectSplit best = {0, 0, FLT_MAX, true};
+    for (int axis = 0; axis < 3; axis++) {   // BLAS.TrySplit's sweep, reading the precomputed costs
+        const float* L = ws.L[axis].data();
+        const float* R = ws.R[axis].data();
+        int firstRight = start + 1;
+        for (int i = end - 1; i >= firstRight; i--)
+            if (R[i] >= best.newCost) { firstRight = i + 1; break; }
+        for (int i = firstRight - 1; i < end - 1; i++) {
+            const int splitIndex = i + 1;
+            const float leftCost = L[i];
+            const float cost = leftCost + R[splitIndex];
+            if (cost < best.newCost) {
+                best.splitIndex = splitIndex;
+                best.axis = axis;
+                best.newCost = cost;
+            } else if (leftCost >= best.newCost) {
+                break;
+            }
+        }
+    }
+    if (best.newCost == FLT_MAX) {
+        best.axis = 0;
+        best.splitIndex = start + parent.TriCount / 2;
+    }
+    if (parent.TriCount <= s.maxLeafTriangleCount) {
+        float notSplitCost = s.triangleCost * (float)parent.TriCount;
+        best.newCost = 1.0f + (s.triangleCost * best.newCost / parentBox.halfArea());
+        if (best.newCost >= notSplitCost) return none;
+    }
+
+    Box childBox[2];
+    runTasks(2, s.threads, [&](int t) {
+        childBox[t] = t == 0 ? computeBoundingBox(start, best.splitIndex - start, bd, best.axis)
+                             : computeBoundingBox(best.splitIndex, end - best.splitIndex, bd, best.axis);
+    });
+    const bool swapSides = childBox[0].halfArea() < childBox[1].halfArea();   // larger child goes left
+
+    uint8_t* table = bd.fragLeftTable.data();
+    int* ids = bd.sorted[best.axis].data();
+    const int split0 = best.splitIndex;
+    runTasks(2, s.threads, [&](int t) {
+        if (t == 0) for (int i = start; i < split0; i++) table[ids[i]] = !swapSides;
+        else for (int i = split0; i < end; i++) table[ids[i]] = swapSides;
+    });
+
+    // three independent id arrays: each needs its own auxiliary range
+    std::vector<int> auxB(parent.TriCount), auxC(parent.TriCount);
+    int newSplit = best.splitIndex;
+    runTasks(3, s.threads, [&](int t) {
+        if (t == 0) { if (swapSides) newSplit = start + stablePartition(ids + start, parent.TriCount, bd.partitionAux.data() + start, table); }
+        else if (t == 1) stablePartition(bd.sorted[(best.axis + 1) % 3].data() + start, parent.TriCount, auxB.data(), table);
+        else stablePartition(bd.sorted[(best.axis + 2) % 3].data() + start, parent.TriCount, auxC.data(), table);
+    });
+    best.splitIndex = newSplit;
+    return best;
+}
+
 // ---------------------------------------------------------------- BLAS.Build
 struct BuildResult {
     std::vector<GpuBlasNode> nodes;
@@ -526,6 +633,10 @@ static int removeEmptySubtrees(BuildResult& blas) {
 }
 
 static int buildBlas(BuildResult& blas, BuildData& bd, const Settings& s) {
+    const bool timing = getenv("IDKHOST_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now(), t1;
+    auto lap = [&](const char* what) { if (timing) { t1 = now(); fprintf(stderr, "[idkhost]   %-14s %8.1f ms\n", what, (t1 - t0) * 1e3); t0 = t1; } };
     blas.nodes[0] = GpuBlasNode{};
     GpuBlasNode& root = blas.nodes[1];
     root = GpuBlasNode{};
@@ -533,43 +644,62 @@ static int buildBlas(BuildResult& blas, BuildData& bd, const Settings& s) {
     root.TriCount = bd.n();
 
     if (s.threads > 1 && bd.n() >= (1 << 14)) {
-        // Breadth phase on one thread until enough independent sub-tasks exist, then a pool.
-        std::vector<BuildTask> tasks;
-        tasks.push_back({1, 2});
+        // Task pool over the tree (BLAS.cs:221-231 runs sub-tasks on separate threads): a worker takes a node; a node
+        // above the threshold is split once and its two children become tasks, a smaller one is finished serially.
+        // Sub-tasks touch disjoint ranges of every array, so any execution order yields the same tree. The one or two
+        // levels where there are fewer nodes than workers use the wide split (all threads on one node).
         const int threshold = std::max(1 << 13, bd.n() / (s.threads * 8)); // BLAS.THREADED_RECURSION_THRESHOLD
-        size_t cursor = 0;
-        std::vector<BuildTask> leafTasks;
-        while (cursor < tasks.size()) {
-            BuildTask t = tasks[cursor++];
-            const GpuBlasNode& n = blas.nodes[t.parentNodeId];
-            if (n.TriCount >= 2 * threshold) {
-                // split this node only (one step), children re-queued
-                std::vector<BuildTask> spill;
-                // run a single step by giving a spill threshold of 0 for this node's children
-                GpuBlasNode& parent = blas.nodes[t.parentNodeId];
-                setBounds(parent, computeBoundingBox(parent.TriStartOrChild, parent.TriCount, bd, 0));
-                ObjectSplit split = trySplit(parent, bd, s);
-                if (!split.valid) continue;
-                GpuBlasNode left = {}; left.TriStartOrChild = parent.TriStartOrChild; left.TriCount = split.splitIndex - left.TriStartOrChild;
-                GpuBlasNode right = {}; right.TriStartOrChild = split.splitIndex; right.TriCount = parent.TriCount - left.TriCount;
-                int leftId = t.newNodesId, rightId = leftId + 1;
-                blas.nodes[leftId] = left; blas.nodes[rightId] = right;
-                parent.TriStartOrChild = leftId; parent.TriCount = 0;
-                tasks.push_back({leftId, rightId + 1});
-                tasks.push_back({rightId, rightId + (2 * left.TriCount - 1)});
-            } else {
-                leafTasks.push_back(t);
+        const int wideThreshold = std::max(2 * threshold, bd.n() / 3);
+        std::mutex mu;
+        std::condition_variable cv;
+        std::vector<BuildTask> queue;
+        int active = 0;
+        queue.push_back({1, 2});
+        auto splitOnce = [&](BuildTask t, WideScratch* wide) {
+            GpuBlasNode& parent = blas.nodes[t.parentNodeId];
+            setBounds(parent, computeBoundingBox(parent.TriStartOrChild, parent.TriCount, bd, 0));
+            ObjectSplit split = wide ? trySplitWide(parent, bd, s, *wide) : trySplit(parent, bd, s);
+            if (!split.valid) return;
+            GpuBlasNode left = {}; left.TriStartOrChild = parent.TriStartOrChild; left.TriCount = split.splitIndex - left.TriStartOrChild;
+            GpuBlasNode right = {}; right.TriStartOrChild = split.splitIndex; right.TriCount = parent.TriCount - left.TriCount;
+            int leftId = t.newNodesId, rightId = leftId + 1;
+            blas.nodes[leftId] = left; blas.nodes[rightId] = right;
+            parent.TriStartOrChild = leftId; parent.TriCount = 0;
+            std::lock_guard<std::mutex> lk(mu);
+            queue.push_back({leftId, rightId + 1});
+            queue.push_back({rightId, rightId + (2 * left.TriCount - 1)});
+        };
+        {   // top of the tree: all threads on one node at a time
+            WideScratch wide;
+            for (;;) {
+                size_t pick = queue.size();
+                for (size_t i = 0; i < queue.size(); i++)
+                    if (blas.nodes[queue[i].parentNodeId].TriCount >= wideThreshold) { pick = i; break; }
+                if (pick == queue.size()) break;
+                BuildTask t = queue[pick];
+                queue.erase(queue.begin() + pick);
+                splitOnce(t, &wide);
             }
         }
-        std::atomic<size_t> next(0);
+        lap("breadth");
         std::vector<std::thread> pool;
         for (int i = 0; i < s.threads; i++) {
             pool.emplace_back([&]() {
+                std::unique_lock<std::mutex> lk(mu);
                 for (;;) {
-                    size_t k = next.fetch_add(1);
-                    if (k >= leafTasks.size()) break;
-                    processSubtree(blas, bd, s, leafTasks[k], nullptr, 0);
+                    while (queue.empty() && active > 0) cv.wait(lk);
+                    if (queue.empty()) break;                       // nothing queued and nobody working: done
+                    BuildTask t = queue.back();
+                    queue.pop_back();
+                    active++;
+                    lk.unlock();
+                    if (blas.nodes[t.parentNodeId].TriCount >= 2 * threshold) splitOnce(t, nullptr);
+                    else processSubtree(blas, bd, s, t, nullptr, 0);
+                    lk.lock();
+                    active--;
+                    cv.notify_all();
                 }
+                cv.notify_all();
             });
         }
         for (auto& th : pool) th.join();
@@ -577,6 +707,7 @@ static int buildBlas(BuildResult& blas, BuildData& bd, const Settings& s) {
         processSubtree(blas, bd, s, {1, 2}, nullptr, 0);
     }
 
+    lap("subtrees");
     if (root.TriCount > 0) {
         blas.nodes[2] = root;
         blas.nodes[3] = root;
@@ -584,7 +715,10 @@ static int buildBlas(BuildResult& blas, BuildData& bd, const Settings& s) {
         root.TriCount = 0;
     }
     optimizeStackSize(blas, s);
-    return removeEmptySubtrees(blas);
+    lap("stack opt");
+    const int used = removeEmptySubtrees(blas);
+    lap("compact");
+    return used;
 }
 
 // ---------------------------------------------------------------- GetUnindexedTriangles
@@ -708,6 +842,10 @@ IdkBlasBuild* idkhost_blas_build(const PackedVec3* positions, uint64_t vertexCou
     s.doPreSplit = settings->DoPreSplit;
     s.threads = std::max(1, settings->Threads);
 
+    const bool timing = getenv("IDKHOST_TIMING") != nullptr;
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    double t0 = now(), t1;
+    auto lap = [&](const char* what) { if (timing) { t1 = now(); fprintf(stderr, "[idkhost] %-14s %8.1f ms\n", what, (t1 - t0) * 1e3); t0 = t1; } };
     Geometry g = {positions, triangles, (int)triangleCount};
     BuildData bd;
     if (s.doPreSplit) {
@@ -716,6 +854,7 @@ IdkBlasBuild* idkhost_blas_build(const PackedVec3* positions, uint64_t vertexCou
         bd.frags.bounds.resize(g.triCount);
         for (int i = 0; i < g.triCount; i++) bd.frags.bounds[i] = boxFromTri(g.tri(i));
     }
+    lap("presplit");
     const int n = bd.n();
     bd.fragLeftTable.assign(n, 0);
     bd.rightCostsAccum.assign(n, 0.0f);
@@ -729,15 +868,19 @@ IdkBlasBuild* idkhost_blas_build(const PackedVec3* positions, uint64_t vertexCou
         for (int a = 0; a < 3; a++) radixSortFragments(bd.frags, a, bd.sorted[a]);
     }
 
+    lap("radix sort");
     BuildResult blas;
     blas.nodes.assign(std::max(2 * n, 4), GpuBlasNode{});
     int used = buildBlas(blas, bd, s);
     blas.nodes.resize(used);
+    lap("build+stackopt");
 
     IdkBlasBuild* out = new IdkBlasBuild();
     if (s.doPreSplit) unindexPreSplit(blas, bd, g, out->tris);
     else unindexPlain(blas, bd, g, out->tris);
+    lap("unindex");
     out->sah = computeGlobalSAH(blas, s);
+    lap("sah");
     out->nodes = std::move(blas.nodes);
     out->requiredStackSize = blas.requiredStackSize;
     out->fragmentCount = n;

@@ -241,3 +241,12 @@ def _models_of_multi_blas():
     """The three models scenes.multi_blas() assembles (room, ball, crate)."""
     from idkengine_b200 import scenes
     return scenes.multi_blas_models()
+
+
+def test_threaded_build_is_deterministic():
+    """The task pool and the wide top-of-tree split must reproduce the serial builder bit for bit."""
+    from idkengine_b200 import scenes
+    a, _ = scenes.atrium(120000, threads=1)
+    for th in (3, 8):
+        b, _ = scenes.atrium(120000, threads=th)
+        assert a.blas_nodes.tobytes() == b.blas_nodes.tobytes() and a.blas_triangles.tobytes() == b.blas_triangles.tobytes(), th
