@@ -378,6 +378,23 @@ def textured_room(threads=None):
     return scene, cam
 
 
+
+def texturize(scene, size=512, count=8, seed=11):
+    """Give every material of an already built scene a base-colour (sRGB) and a metallic-roughness texture out of `count`
+    procedural size x size images and planar texcoords, e.g. to measure the textured shade path on the bench atrium."""
+    rng = np.random.default_rng(seed)
+    handles = []
+    for k in range(count):
+        img = _checker(size, 8 << (k % 3), rng.integers(60, 255, 3), rng.integers(20, 200, 3), seed=seed + k)
+        handles.append((scene.add_texture(img, srgb=True), scene.add_texture(rng.integers(0, 256, (size // 4, size // 4, 4)).astype(np.uint8))))
+    for m in range(len(scene.materials)):
+        scene.materials["BaseColorTexture"][m], scene.materials["MetallicRoughnessTexture"][m] = handles[m % count]
+    x, y, z = scene.positions["x"], scene.positions["y"], scene.positions["z"]
+    scene.vertices["TexCoord"][:, 0] = x * 0.23 + z * 0.17
+    scene.vertices["TexCoord"][:, 1] = y * 0.21 + z * 0.11 - x * 0.05
+    return scene
+
+
 # --------------------------------------------------------------------------- real Sponza (local only)
 REFERENCE_SPONZA = "/root/reference/IDKEngine/Resource/Models/SponzaCompressed/Sponza.gltf"
 

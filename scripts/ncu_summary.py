@@ -35,10 +35,17 @@ def launches(path):
     ki, vi, mi = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name")
     seq = [(r[ki].split("(")[0].replace("void ", ""), float(r[vi].replace(",", ""))) for r in rows[1:] if r[mi] == "gpu__time_duration.sum"]
     print(f"# {path}: {len(seq)} launches (ncu --metrics gpu__time_duration.sum --clock-control none; cold-cache, serialised: compare SHARES)")
+    gi = hdr.index("Grid Size")
+    grids = [int(r[gi].strip("()").split(",")[0]) for r in rows[1:] if r[mi] == "gpu__time_duration.sum"]
     starts = [i for i, (k, _) in enumerate(seq) if k.startswith("k_raygen") or k.startswith("k_vx_clear")]
-    if len(starts) >= 2:
-        a, b = starts[-2], starts[-1]
-        print(f"# one full step (launches {a}..{b - 1}):")
+    steps = [(starts[j], starts[j + 1]) for j in range(len(starts) - 1)]
+
+    def trav_grid(a, b):
+        g = [grids[i] for i in range(a, b) if seq[i][0].startswith("k_traverse2")]
+        return max(g) if g else 0
+
+    def show(a, b, title):
+        print(f"# {title} (launches {a}..{b - 1}, k_traverse2 grid {trav_grid(a, b)} blocks):")
         tot = defaultdict(float)
         for k, v in seq[a:b]:
             print(f"{k:44s} {v / 1000:10.1f} us")
@@ -47,6 +54,18 @@ def launches(path):
         print("# shares of the step:")
         for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
             print(f"{k:44s} {v / 1000:10.1f} us {v / T * 100:6.1f} %")
+
+    if steps:
+        # bench.py runs the same step in two modes: serial (full persistent grids; the pass the per-kernel numbers and the
+        # roofline come from) and pipelined (each lane's traversal grid = its share of the resident blocks; ncu serialises the
+        # lanes, so those launches look slow here although they overlap in the real run)
+        plain = [st for st in steps if not any("<1" in seq[i][0] for i in range(*st))] or steps
+        full_grid = max(trav_grid(*st) for st in plain)
+        serial = [st for st in plain if trav_grid(*st) == full_grid]
+        show(*serial[-1], "one full step of the serial pass")
+        lane = [st for st in plain if 0 < trav_grid(*st) < full_grid]
+        if lane:
+            show(*lane[-1], "one step of the pipelined pass (lane-sized grids, serialised by ncu)")
     tot = defaultdict(lambda: [0, 0.0])
     for k, v in seq:
         tot[k][0] += 1
