@@ -1,0 +1,31 @@
+// Compile + link check of the C++ host mirror (include/idkpt.hpp). Without a CUDA device the constructor must throw
+// idk::Error(IDKPT_ERR_NO_DEVICE): the product has no CPU fallback. With a device it renders nothing (no scene) and checks
+// that Compute() without a scene reports IDKPT_ERR_NO_SCENE.
+#include <cstdio>
+#include <cstring>
+
+#include "idkpt.hpp"
+
+int main() {
+    static_assert(sizeof(IdkPtSettings) == 40, "IdkPtSettings layout");
+    try {
+        idk::PathTracer pt(64, 48);
+        GpuPerFrameData frame;
+        std::memset(&frame, 0, sizeof(frame));
+        try {
+            pt.Compute(frame);
+            std::puts("FAIL: Compute without a scene succeeded");
+            return 1;
+        } catch (const idk::Error& e) {
+            if (e.status() != IDKPT_ERR_NO_SCENE) { std::printf("FAIL: status %d\n", e.status()); return 1; }
+        }
+        pt.RayDepth(5);
+        if (pt.RayDepth() != 5 || pt.AccumulatedSamples() != 0) return 1;
+        std::puts("OK device");
+        return 0;
+    } catch (const idk::Error& e) {
+        if (e.status() == IDKPT_ERR_NO_DEVICE) { std::printf("OK no-device: %s\n", e.what()); return 0; }
+        std::printf("FAIL: %d %s\n", e.status(), e.what());
+        return 1;
+    }
+}

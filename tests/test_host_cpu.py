@@ -206,3 +206,15 @@ def test_oracle_any_hit_and_shadows(multi_blas):
     assert (vis[depth == 1.0] == 7.0).all()
     inside = vis[depth < 1.0]
     assert ((inside >= 0.0) & (inside <= 1.0)).all() and (inside == 0.0).any() and (inside == 1.0).any()
+
+
+def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """include/idkpt.hpp (the C++ stand-in for the C# PathTracerNative) against the built library."""
+    exe = str(tmp_path / "hpp_smoke")
+    libdir = os.path.dirname(build.LIBIDKPT)
+    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "tests", "cpp", "hpp_smoke.cpp"),
+           "-L", libdir, "-lidkpt", "-Wl,-rpath," + libdir, "-o", exe]
+    subprocess.run(cmd, check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert r.stdout.startswith("OK")
