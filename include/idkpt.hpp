@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "idkpt.h"
+#include "idkvx.h"
 
 namespace idk {
 
@@ -184,6 +185,52 @@ private:
     IdkPtCtx* ctx_ = nullptr;
     IdkPtSettings settings_;
     int width_, height_;
+};
+
+// Voxelizer.Render() + ConeTracer.Compute() (Source/Render/VXGI/Voxelizer/Voxelizer.cs:57-114, ConeTracing/ConeTracer.cs:10-50)
+class Voxelizer {
+public:
+    Voxelizer(int width, int height, int depth, const float gridMin[3], const float gridMax[3], int device = 0) {
+        IdkVxCreateInfo ci = {};
+        ci.Device = device; ci.Width = width; ci.Height = height; ci.Depth = depth;
+        for (int i = 0; i < 3; i++) { ci.GridMin[i] = gridMin[i]; ci.GridMax[i] = gridMax[i]; }
+        const int rc = idkvx_create(&ci, &ctx_);
+        if (rc != IDKPT_OK) {
+            const char* msg = idkvx_last_error(nullptr);
+            throw Error(rc, std::string("idkvx_create failed: ") + (msg ? msg : ""));
+        }
+    }
+    ~Voxelizer() { Dispose(); }
+    Voxelizer(const Voxelizer&) = delete;
+    Voxelizer& operator=(const Voxelizer&) = delete;
+    void Dispose() { if (ctx_) { idkvx_destroy(ctx_); ctx_ = nullptr; } }
+
+    void SetScene(const IdkPtSceneDesc& scene) { check(idkvx_set_scene(ctx_, &scene), "idkvx_set_scene"); }
+    void SetGrid(const float gridMin[3], const float gridMax[3]) { check(idkvx_set_grid(ctx_, gridMin, gridMax), "idkvx_set_grid"); }   // GridMin / GridMax setters
+    int LevelCount() const { return idkvx_level_count(ctx_); }
+    IdkVxStats Render() { IdkVxStats st = {}; check(idkvx_voxelize(ctx_, &st), "idkvx_voxelize"); return st; }
+    // ConeTracer.Compute: G-buffer attachments in, rgba32f indirect light out (width * height * 4 floats)
+    std::vector<float> ConeTrace(const GpuPerFrameData& frame, const IdkVxConeSettings& settings, const float* depth, const float* normalRG,
+                                 const float* metallicRoughness, int width, int height, const float skyColor[3], IdkVxStats* stats = nullptr) {
+        std::vector<float> out((size_t)width * height * 4);
+        check(idkvx_cone_trace(ctx_, &frame, &settings, depth, normalRG, metallicRoughness, width, height, skyColor, out.data(), stats), "idkvx_cone_trace");
+        return out;
+    }
+    // ConeTracer.GpuSettings defaults (ConeTracer.cs:10-22)
+    static IdkVxConeSettings DefaultConeSettings() {
+        IdkVxConeSettings c = {};
+        c.MaxSamples = 4; c.StepMultiplier = 0.16f; c.GIBoost = 1.3f; c.GISkyBoxBoost = 1.0f / 1.3f; c.NormalRayOffset = 1.0f; c.NoiseIndex = 0;
+        return c;
+    }
+
+private:
+    void check(int rc, const char* what) const {
+        if (rc != IDKPT_OK) {
+            const char* msg = idkvx_last_error(ctx_);
+            throw Error(rc, std::string(what) + " failed: " + (msg ? msg : ""));
+        }
+    }
+    IdkVxCtx* ctx_ = nullptr;
 };
 
 }  // namespace idk

@@ -21,6 +21,10 @@ int main() {
         }
         pt.RayDepth(5);
         if (pt.RayDepth() != 5 || pt.AccumulatedSamples() != 0) return 1;
+        const float mn[3] = {-1, -1, -1}, mx[3] = {1, 1, 1};
+        idk::Voxelizer vx(16, 16, 16, mn, mx);
+        if (vx.LevelCount() != 5) return 1;
+        try { vx.Render(); return 1; } catch (const idk::Error& e) { if (e.status() != IDKPT_ERR_NO_SCENE) return 1; }
         std::puts("OK device");
         return 0;
     } catch (const idk::Error& e) {

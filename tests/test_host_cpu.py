@@ -212,7 +212,7 @@ def test_cpp_host_mirror_compiles_links_and_fails_loudly_without_gpu(tmp_path):
     """include/idkpt.hpp (the C++ stand-in for the C# PathTracerNative) against the built library."""
     exe = str(tmp_path / "hpp_smoke")
     libdir = os.path.dirname(build.LIBIDKPT)
-    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "tests", "cpp", "hpp_smoke.cpp"),
+    cmd = ["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-Wno-comment", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "tests", "cpp", "hpp_smoke.cpp"),
            "-L", libdir, "-lidkpt", "-Wl,-rpath," + libdir, "-o", exe]
     subprocess.run(cmd, check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
