@@ -183,16 +183,26 @@ static float getNodeSize(float extent, float globalSize) {
 }
 
 static void preSplit(const Geometry& g, const Settings& s, Fragments& out) {
+    // Priorities once (the reference evaluates GetPriority three times per triangle); the total is summed in triangle order
+    // on one thread, exactly as PreSplitting.cs:33-37 does, because float addition order matters.
+    std::vector<float> prio((size_t)g.triCount);
+    auto chunked = [&](auto&& f) {
+        const int workers = std::max(1, std::min(s.threads, g.triCount / 4096 + 1));
+        if (workers == 1) { f(0, g.triCount); return; }
+        std::vector<std::thread> pool;
+        const int per = (g.triCount + workers - 1) / workers;
+        for (int w = 0; w < workers; w++) pool.emplace_back([&, w]() { f(std::min(g.triCount, w * per), std::min(g.triCount, (w + 1) * per)); });
+        for (auto& t : pool) t.join();
+    };
+    chunked([&](int b0, int e0) { for (int i = b0; i < e0; i++) prio[i] = priority(g.tri(i)); });
     float totalPriority = 0.0f;
-    for (int i = 0; i < g.triCount; i++) totalPriority += priority(g.tri(i));
+    for (int i = 0; i < g.triCount; i++) totalPriority += prio[i];
 
-    size_t counter = 0;
-    for (int i = 0; i < g.triCount; i++)
-        counter += getSplitCount(priority(g.tri(i)), totalPriority, g.triCount, s.splitFactor);
-
-    out.bounds.resize(counter);
-    out.originalTriIds.resize(counter);
-    counter = 0;
+    // every triangle emits exactly its split count (left + right counts always add up), so the output offsets are a prefix sum
+    std::vector<size_t> offset((size_t)g.triCount + 1, 0);
+    for (int i = 0; i < g.triCount; i++) offset[i + 1] = offset[i] + (size_t)getSplitCount(prio[i], totalPriority, g.triCount, s.splitFactor);
+    out.bounds.resize(offset[g.triCount]);
+    out.originalTriIds.resize(offset[g.triCount]);
 
     Box globalBox = Box::empty();
     for (int i = 0; i < g.triCount; i++) {
@@ -202,10 +212,12 @@ static void preSplit(const Geometry& g, const Settings& s, Fragments& out) {
     float globalSize[3] = {globalBox.size(0), globalBox.size(1), globalBox.size(2)};
 
     struct Item { Box box; int splits; };
+    chunked([&](int b0, int e0) {
     std::vector<Item> stack(64 + 4096);
-    for (int i = 0; i < g.triCount; i++) {
+    for (int i = b0; i < e0; i++) {
         Tri tri = g.tri(i);
-        int splitCount = getSplitCount(priority(tri), totalPriority, g.triCount, s.splitFactor);
+        size_t counter = offset[i];
+        int splitCount = (int)(offset[i + 1] - offset[i]);
         int sp = 0;
         stack[sp++] = {boxFromTri(tri), splitCount};
         while (sp > 0) {
@@ -241,6 +253,7 @@ static void preSplit(const Geometry& g, const Settings& s, Fragments& out) {
             stack[sp++] = {lBox, leftCount};
         }
     }
+    });
 }
 
 // ---------------------------------------------------------------- BLAS.GetBuildData
