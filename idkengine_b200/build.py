@@ -15,7 +15,7 @@ REPO_DIR = os.path.dirname(PKG_DIR)
 INCLUDE_DIR = os.path.join(REPO_DIR, "include")
 
 CSRC_DIR = os.path.join(PKG_DIR, "csrc")
-HOST_DIR = os.path.join(PKG_DIR, "host")
+HOST_DIR = os.path.join(PKG_DIR, "host_mirror")
 LIBIDKPT = os.path.join(CSRC_DIR, "libidkpt.so")
 LIBIDKHOST = os.path.join(HOST_DIR, "libidkhost.so")
 

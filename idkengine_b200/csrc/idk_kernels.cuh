@@ -762,10 +762,14 @@ struct ShadeArgs {
     int outputAovs;
 };
 
-// status word: [63:34] epoch, [33:32] flag (1 = aggregate, 2 = inclusive prefix), [31:0] value
+// status word: [63:34] epoch (30 bits), [33:32] flag (1 = aggregate, 2 = inclusive prefix), [31:0] value.
+// The host hands out epochs in [1, IDK_EPOCH_MASK] per lane and clears the status words when the counter wraps, so a
+// stale word can never look like the current epoch (pack and compare go through the same 30-bit helpers).
+#define IDK_EPOCH_MASK 0x3FFFFFFFu
 __device__ __forceinline__ unsigned long long pack_status(uint32_t epoch, uint32_t flag, uint32_t value) {
-    return ((unsigned long long)epoch << 34) | ((unsigned long long)flag << 32) | value;
+    return ((unsigned long long)(epoch & IDK_EPOCH_MASK) << 34) | ((unsigned long long)flag << 32) | value;
 }
+__device__ __forceinline__ uint32_t status_epoch(unsigned long long sv) { return (uint32_t)(sv >> 34) & IDK_EPOCH_MASK; }
 
 // One thread per alive ray, no block-level cooperation: every warp runs at its own pace (the ordered compaction of
 // the reference's atomic alive list is a separate, uniform-cost pass over 4-byte entries: k_compact).
@@ -1090,7 +1094,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_compact(CompactArgs a) {
                 int look = (int)tile - 1;
                 while (look >= 0) {
                     const unsigned long long sv = *((volatile unsigned long long*)&a.tileStatus[look]);
-                    if ((uint32_t)(sv >> 34) != a.epoch) continue;              // not published yet
+                    if (status_epoch(sv) != (a.epoch & IDK_EPOCH_MASK)) continue;   // not published yet
                     const uint32_t flag = (uint32_t)(sv >> 32) & 3u;
                     exclusive += (uint32_t)sv;
                     if (flag == 2u) break;
@@ -1146,12 +1150,15 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_accumulate_scatter(const float4* 
                                                                   uint32_t count, uint32_t accumulatedSamples, int debugTraversal,
                                                                   GatherArgs g);
 
-__global__ void __launch_bounds__(32) k_gather_wait(const uint32_t* flags, int world, uint32_t epoch, uint32_t* timedOut) {
+// timeoutCycles: SM clocks (idkpt.cu: IDKPT_GATHER_TIMEOUT_MS, default 30 s). Peers only have to have called
+// idkpt_gather_import before their first gathered Compute; a rank that is still uploading its scene just makes the others
+// wait here. After a timeout the frame is lost and the ranks' gather epochs may disagree: re-run export/import.
+__global__ void __launch_bounds__(32) k_gather_wait(const uint32_t* flags, int world, uint32_t epoch, uint32_t* timedOut, long long timeoutCycles) {
     const int p = threadIdx.x;
     if (p < world) {
         const long long t0 = clock64();
         while (*((volatile const uint32_t*)&flags[p]) != epoch) {
-            if (clock64() - t0 > 6000000000ll) { *timedOut = 1u; break; }   // ~3 s: a peer died; fail instead of hanging the GPU
+            if (clock64() - t0 > timeoutCycles) { *timedOut = 1u; break; }   // a peer died; fail instead of hanging the GPU
         }
     }
     __threadfence_system();

@@ -39,6 +39,7 @@ struct Lane {
     DevBuf countsDev;              // uint32 counts[IDKPT_MAX_RAY_DEPTH + 1]
     DevBuf tickets;                // uint32 tickets[2 * (IDKPT_MAX_RAY_DEPTH + 1)] (traverse, compact)
     DevBuf tileStatus;             // u64 per tile
+    uint32_t epoch = 0;            // compaction epoch of this lane's status words: 1 .. IDK_EPOCH_MASK, cleared on wrap
     DevBuf keys;                   // ray sorting: key per slot of the compacted alive list
     IdkSortScratch sortScratch;
 };
@@ -90,7 +91,7 @@ struct IdkPtCtx {
     DevBuf images[3];
     DevBuf counters;               // TraceCounters
     DevBuf countLog;               // per-sample copies of the alive counts (stats only)
-    uint32_t epoch = 0;
+    uint32_t epochStart = 0;       // IDKPT_DEBUG_EPOCH_START: first compaction epoch of a fresh lane (wrap-around test hook)
     bool exportEnabled = false;
 
     // launch configuration
@@ -105,6 +106,7 @@ struct IdkPtCtx {
     int treeletNodes = 0;
 
     std::vector<cudaEvent_t> events;
+    cudaStreamAttrValue l2Window = {};   // persisting-L2 window over [nodes | triRec]; applied to the main stream and every lane stream
 
     // multi-GPU gather over NVLink peer memory (CUDA IPC): full-size images (double-buffered) + arrival flags per rank
     int gatherWorld = 0, gatherRank = 0;
@@ -113,6 +115,8 @@ struct IdkPtCtx {
     void* peerFlags[2][IDK_MAX_PEERS] = {};
     bool peerMapped[IDK_MAX_PEERS] = {};
     uint32_t gatherEpoch = 0;
+    double gatherTimeoutMs = 30000.0;                                     // arrival wait bound (IDKPT_GATHER_TIMEOUT_MS); a dead peer becomes an error, not a hung GPU
+    int clockKHz = 1965000;
     int gatherCurrent = -1;                                               // buffer holding the last completed frame
 
     // asynchronous presentation (device snapshot + D2H on a second stream, overlapping the next Compute)
@@ -262,6 +266,8 @@ static int allocate_lane(IdkPtCtx* ctx, Lane& ln) {
     if (!ln.radianceReady) CK(cudaEventCreateWithFlags(&ln.radianceReady, cudaEventDisableTiming));
     if (!ln.accDone) CK(cudaEventCreateWithFlags(&ln.accDone, cudaEventDisableTiming));
     CK(cudaStreamSynchronize(ctx->stream));   // the status words are cleared before any lane stream touches them
+    ln.epoch = ctx->epochStart;
+    CK(cudaStreamSetAttribute(ln.stream, cudaStreamAttributeAccessPolicyWindow, &ctx->l2Window));   // BVH persistence on the lane streams too
     ln.accPending = false;
     ln.allocated = true;
     return IDKPT_OK;
@@ -331,7 +337,6 @@ static int allocate_wavefront(IdkPtCtx* ctx) {
         CK(cudaMemsetAsync(ctx->images[i].p, 0, n * 16, ctx->stream));   // Result.Fill(0), PathTracer.cs:305
     }
     CK(ensure(ctx->counters, sizeof(TraceCounters)));
-    ctx->epoch = 0;
     return IDKPT_OK;
 }
 
@@ -512,6 +517,9 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
     if (const char* v = getenv("IDKPT_TUNE_LEAF")) ctx->tune.leafThreshold = std::max(1, std::min(32, atoi(v)));
     if (const int fl = (ci->Flags >> 8) & 15) ctx->laneCount = std::min(IDK_MAX_LANES, fl);   // IDKPT_CREATE_LANES(n)
     if (const char* v = getenv("IDKPT_LANES")) ctx->laneCount = std::max(1, std::min(IDK_MAX_LANES, atoi(v)));
+    if (const char* v = getenv("IDKPT_DEBUG_EPOCH_START")) ctx->epochStart = (uint32_t)strtoul(v, nullptr, 0) & IDK_EPOCH_MASK;
+    if (const char* v = getenv("IDKPT_GATHER_TIMEOUT_MS")) ctx->gatherTimeoutMs = std::max(1.0, atof(v));
+    ctx->clockKHz = prop.clockRate;
     compute_tile_rows(ctx);
     int rc = allocate_wavefront(ctx);
     if (rc != IDKPT_OK) {
@@ -586,6 +594,21 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
         return strstr(terr, "not supported") ? IDKPT_ERR_UNSUPPORTED : IDKPT_ERR_INVALID_ARGUMENT;
     }
 
+    // triangle vertex ids must index the position / vertex arrays
+    // (checked on the host copy: cheap relative to the BVH build that produced it)
+    for (uint64_t i = 0; i < s->BlasTriangleCount; i++) {
+        const GpuBlasTriangle& t = s->BlasTriangles[i];
+        const uint64_t lim = std::min(s->VertexPositionCount, s->VertexCount);
+        if ((uint64_t)(uint32_t)t.X >= lim || (uint64_t)(uint32_t)t.Y >= lim || (uint64_t)(uint32_t)t.Z >= lim || t.MeshId < 0 || (uint64_t)t.MeshId >= s->MeshCount)
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuBlasTriangle index out of range");
+    }
+    if ((size_t)std::max(1, s->BlasStackSize) * IDK_BLOCK * sizeof(uint32_t) > 200 * 1024)
+        return fail(ctx, IDKPT_ERR_UNSUPPORTED, "BlasStackSize too large for the shared-memory traversal stack");
+
+    // Every host-side check has passed; from here on device arrays are overwritten / reallocated. Until the new scene is
+    // complete the context has NO scene: a failure below (CUDA error, out of memory) must not leave the previous scene's
+    // pointers and counts looking valid.
+    ctx->haveScene = false;
     int rc;
     // nodes and triangle records share one allocation ("bvh"): [nodes | triRec], so that one L2 access-policy window covers both
     const size_t nodeBytes = ((s->BlasNodeCount * sizeof(GpuBlasNode)) + 255) & ~(size_t)255;
@@ -619,14 +642,6 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     ctx->hostMaterialMaxHandle.assign(s->MaterialCount, 0);
     for (uint64_t i = 0; i < s->MaterialCount; i++) ctx->hostMaterialMaxHandle[i] = material_max_handle(s->Materials[i]);
 
-    // triangle vertex ids must index the position / vertex arrays
-    // (checked on the host copy: cheap relative to the BVH build that produced it)
-    for (uint64_t i = 0; i < s->BlasTriangleCount; i++) {
-        const GpuBlasTriangle& t = s->BlasTriangles[i];
-        const uint64_t lim = std::min(s->VertexPositionCount, s->VertexCount);
-        if ((uint64_t)(uint32_t)t.X >= lim || (uint64_t)(uint32_t)t.Y >= lim || (uint64_t)(uint32_t)t.Z >= lim || t.MeshId < 0 || (uint64_t)t.MeshId >= s->MeshCount)
-            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: GpuBlasTriangle index out of range");
-    }
     CK(ensure(ctx->vtxFrame, std::max<size_t>(s->VertexCount, 1) * 32));
     CK(ensure(ctx->surfRec, std::max<size_t>(s->MeshCount, 1) * 80));
     if (s->VertexCount) {
@@ -680,7 +695,7 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
         CK(cudaGetDeviceProperties(&prop, ctx->device));
         const char* env = getenv("IDKPT_L2_PERSIST");
         const bool want = !(env && atoi(env) == 0);
-        cudaStreamAttrValue attr;
+        cudaStreamAttrValue& attr = ctx->l2Window;
         memset(&attr, 0, sizeof(attr));
         if (want && prop.persistingL2CacheMaxSize > 0 && prop.accessPolicyMaxWindowSize > 0) {
             const size_t bvhBytes = nodeBytes + triRecBytes;
@@ -696,6 +711,8 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
             attr.accessPolicyWindow.num_bytes = 0;
         }
         CK(cudaStreamSetAttribute(ctx->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        for (int i = 0; i < IDK_MAX_LANES; i++)    // the asynchronous path launches traverse / shade on the lane streams
+            if (ctx->lanes[i].stream) CK(cudaStreamSetAttribute(ctx->lanes[i].stream, cudaStreamAttributeAccessPolicyWindow, &attr));
     }
     CK(cudaStreamSynchronize(ctx->stream));
     ctx->haveScene = true;
@@ -719,7 +736,7 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
         case IDKPT_ARRAY_TLAS_NODES: b = &ctx->tlas; elem = sizeof(GpuTlasNode); limit = ctx->counts.UseTlas ? ctx->counts.TlasNodeCount : 0; break;
         default: return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: unknown array id");
     }
-    if (first + count > limit) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: range outside the array");
+    if (first > limit || count > limit - first) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: range outside the array");
     if (which == IDKPT_ARRAY_MESHES) {
         const GpuMesh* m = (const GpuMesh*)data;
         for (uint64_t i = 0; i < count; i++)
@@ -1023,7 +1040,11 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                 ca.countOut = counts + j + 1;
                 ca.ticket = tickets + 2 * j + 1;
                 ca.tileStatus = (unsigned long long*)ln.tileStatus.p;
-                ca.epoch = ++ctx->epoch;
+                if (ln.epoch >= IDK_EPOCH_MASK) {   // 30-bit epoch wrapped: clear this lane's status words (ordered on its stream) and restart at 1
+                    CK(cudaMemsetAsync(ln.tileStatus.p, 0, ln.tileStatus.bytes, ls));
+                    ln.epoch = 0;
+                }
+                ca.epoch = ++ln.epoch;
                 k_compact<<<ctx->compactBlocks, IDK_BLOCK, 0, ls>>>(ca);
                 launches++;
             }
@@ -1055,7 +1076,8 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                 k_accumulate_aov<<<accBlocks, IDK_BLOCK, 0, ctx->stream>>>((const float4*)ln.aovAlbedoFinal.p, (const float4*)ln.aovNormalFinal.p,
                                                                            (float4*)ctx->images[1].p, (float4*)ctx->images[2].p, n, ctx->accumulatedSamples);
             if (async) { CK(cudaEventRecord(ln.accDone, ctx->stream)); ln.accPending = true; }   // before the arrival wait: the lane may go on
-            k_gather_wait<<<1, 32, 0, ctx->stream>>>((const uint32_t*)ctx->gatherFlags[b].p, ctx->gatherWorld, g.epoch, (uint32_t*)ctx->gatherScratch.p + 1);
+            k_gather_wait<<<1, 32, 0, ctx->stream>>>((const uint32_t*)ctx->gatherFlags[b].p, ctx->gatherWorld, g.epoch, (uint32_t*)ctx->gatherScratch.p + 1,
+                                                     (long long)(ctx->gatherTimeoutMs * (double)ctx->clockKHz));
             ctx->gatherCurrent = b;
             launches += aovs ? 3 : 2;
         } else {
@@ -1499,7 +1521,7 @@ IDKPT_API int idkpt_read_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t first
         default: return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_range: array id not readable");
     }
     if (which == IDKPT_ARRAY_BLAS_NODES && ctx->treeletNodes) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_read_range: BLAS nodes are re-laid out (IDKPT_TREELET_PAIRS)");
-    if (first + count > limit) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_range: range outside the array");
+    if (first > limit || count > limit - first) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_read_range: range outside the array");
     CK(cudaSetDevice(ctx->device));
     if (count) CK(cudaMemcpyAsync(out, (const char*)b->p + first * elem, count * elem, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

@@ -106,7 +106,7 @@ def build_blas(positions, triangles, presplit=True, threads=None, settings=None)
 
 
 # --------------------------------------------------------------------------- on-disk BLAS cache (include/idkhost_cache.h)
-BUILDER_VERSION = 1          # bump when host/bvh_build.cpp changes its output
+BUILDER_VERSION = 1          # bump when host_mirror/bvh_build.cpp changes its output
 CACHE_BLAS_NODES, CACHE_BLAS_TRIANGLES, CACHE_BUILD_INFO = 1, 2, 100
 CACHE_OK, CACHE_ERR_IO, CACHE_ERR_FORMAT, CACHE_ERR_KEY, CACHE_ERR_CHECKSUM = 0, -1, -2, -3, -4
 

@@ -49,6 +49,86 @@ def test_integration_doc_names_every_entry_point():
     assert not missing, missing
 
 
+# ---- INTEGRATION.md's C# structs vs include/idkpt.h (field names, order, offsets, sizes) -------------------------------------
+_C_SIZES = {"int32_t": 4, "uint32_t": 4, "float": 4, "uint64_t": 8, "int64_t": 8, "uint8_t": 1, "IdkPtGpuSettings": 20}
+_CS_SIZES = {"int": 4, "uint": 4, "float": 4, "ulong": 8, "long": 8, "nint": 8, "byte": 1, "PathTracer.GpuSettings": 20}
+
+
+def _layout(fields):
+    """fields: [(name, elem_size, count, align)] -> [(name, offset, bytes)] with natural (C / LayoutKind.Sequential) alignment."""
+    out, off, amax = [], 0, 1
+    for name, size, count, align in fields:
+        off = (off + align - 1) // align * align
+        out.append((name, off, size * count))
+        off += size * count
+        amax = max(amax, align)
+    return out, (off + amax - 1) // amax * amax
+
+
+def _c_struct_fields(hdr, name):
+    body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (name, name), hdr, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"(?:const )?([\w ]+?)\s*(\*?)\s*((?:\w+(?:\[\w+\])?(?:\s*,\s*)?)+)$", decl)
+        assert m, decl
+        ctype, ptr, names = m.group(1).strip(), m.group(2), m.group(3)
+        for n in names.split(","):
+            n = n.strip()
+            count = 1
+            am = re.match(r"(\w+)\[(\w+)\]", n)
+            if am:
+                n, count = am.group(1), {"IDKPT_MAX_RAY_DEPTH": 64}.get(am.group(2)) or int(am.group(2))
+            size = 8 if ptr else _C_SIZES[ctype]
+            fields.append((n, size, count, min(size, 8) if ctype != "IdkPtGpuSettings" or ptr else 4))
+    return fields
+
+
+def _cs_struct_fields(doc, name):
+    body = re.search(r"public struct %s\s*\{(.*?)\}" % name, doc, re.S).group(1)
+    body = re.sub(r"//[^\n]*|/\*.*?\*/", "", body, flags=re.S)
+    fields = []
+    for decl in body.split(";"):
+        decl = " ".join(decl.split())
+        if not decl:
+            continue
+        m = re.match(r"public (fixed )?([\w\.]+?)(\*?) (.+)$", decl)
+        assert m, decl
+        fixed, ctype, ptr, names = m.groups()
+        for n in names.split(","):
+            n = n.strip()
+            count = 1
+            am = re.match(r"(\w+)\[(\d+)\]", n)
+            if am:
+                assert fixed, decl
+                n, count = am.group(1), int(am.group(2))
+            size = 8 if ptr else _CS_SIZES[ctype]
+            fields.append((n, size, count, 4 if ctype == "PathTracer.GpuSettings" and not ptr else min(size, 8)))
+    return fields
+
+
+def test_integration_doc_structs_match_the_c_header():
+    """Every [StructLayout] struct of INTEGRATION.md section 1 must be byte-compatible with its C twin in include/idkpt.h:
+    same field names in the same order at the same offsets, same total size (the round-1 doc missed Textures/TextureCount)."""
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    hdr = open(os.path.join(REPO, "include", "idkpt.h")).read()
+    cs_names = re.findall(r"\[StructLayout\(LayoutKind\.Sequential\)\]\s*public struct (\w+)", doc)
+    c_names = [n for n in re.findall(r"typedef struct (IdkPt\w+) \{", hdr)]
+    assert sorted("IdkPt" + n for n in cs_names) == sorted(c_names), (cs_names, c_names)
+    ctypes_twins = {"IdkPtCreateInfo": capi.IdkPtCreateInfo, "IdkPtSceneDesc": capi.IdkPtSceneDesc, "IdkPtSettings": capi.IdkPtSettings,
+                    "IdkPtStats": capi.IdkPtStats}
+    for n in cs_names:
+        cl, csize = _layout(_c_struct_fields(hdr, "IdkPt" + n))
+        sl, ssize = _layout(_cs_struct_fields(doc, n))
+        assert cl == sl, (n, cl, sl)
+        assert csize == ssize, (n, csize, ssize)
+        if "IdkPt" + n in ctypes_twins:      # and the ctypes twin the tests call through agrees with both
+            assert ctypes.sizeof(ctypes_twins["IdkPt" + n]) == csize, n
+
+
 def test_no_cpu_fallback(libidkpt):
     import torch
     if torch.cuda.is_available():
