@@ -64,7 +64,7 @@ class IdkPtStats(ctypes.Structure):
                 ("TotalMs", c_f), ("TraverseMs", c_f), ("ShadeMs", c_f), ("SortMs", c_f), ("OtherMs", c_f),
                 ("KernelLaunches", c_u32), ("TraverseLaunches", c_u32),
                 ("BounceTraverseMs", c_f * IDKPT_MAX_RAY_DEPTH), ("BounceShadeMs", c_f * IDKPT_MAX_RAY_DEPTH),
-                ("BounceMaxSteps", c_u32 * IDKPT_MAX_RAY_DEPTH)]
+                ("BounceMaxSteps", c_u32 * IDKPT_MAX_RAY_DEPTH), ("CompactMs", c_f), ("AccumulateMs", c_f)]
 
     def as_dict(self):
         arrays = ("BounceRays", "BounceTraverseMs", "BounceShadeMs", "BounceMaxSteps")
@@ -86,6 +86,7 @@ EXPORTS = [
     "idkpt_create", "idkpt_destroy", "idkpt_last_error", "idkpt_set_scene", "idkpt_update_range", "idkpt_set_sky", "idkpt_set_textures",
     "idkpt_resize", "idkpt_reset_accumulation", "idkpt_accumulated_samples", "idkpt_set_accumulated_samples",
     "idkpt_compute", "idkpt_sync", "idkpt_stream_handle", "idkpt_read_result", "idkpt_write_result", "idkpt_present_async", "idkpt_present_wait",
+    "idkpt_register_host_buffer", "idkpt_unregister_host_buffer",
     "idkpt_gather_export", "idkpt_gather_import", "idkpt_gather_device_ptr",
     "idkpt_result_device_ptr", "idkpt_tile_rows",
     "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_trace_rays_any", "idkpt_shadows_ray_traced",
@@ -189,7 +190,7 @@ def load(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or _build.LIBIDKPT
+    path = path or os.environ.get("IDKPT_LIB") or _build.LIBIDKPT     # IDKPT_LIB: an experiment build (scripts/variant_probe.py)
     if not os.path.exists(path):
         raise RuntimeError(f"{path} is missing: build it with `python -m idkengine_b200.build` "
                            "(libidkpt has no CPU fallback)")
@@ -225,6 +226,10 @@ def load(path=None):
     L.idkpt_present_async.argtypes = [c_vp, c_i32, c_vp, c_u64]
     L.idkpt_present_wait.restype = c_i32
     L.idkpt_present_wait.argtypes = [c_vp]
+    L.idkpt_register_host_buffer.restype = c_i32
+    L.idkpt_register_host_buffer.argtypes = [c_vp, c_vp, c_u64]
+    L.idkpt_unregister_host_buffer.restype = c_i32
+    L.idkpt_unregister_host_buffer.argtypes = [c_vp, c_vp]
     L.idkpt_gather_export.restype = c_i32
     L.idkpt_gather_export.argtypes = [c_vp, c_vp, c_u64]
     L.idkpt_gather_import.restype = c_i32

@@ -265,3 +265,55 @@ __device__ __forceinline__ bool ray_sphere(f3 o, f3 d, f3 position, float radius
 }
 
 __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
+
+// ---- experiment switches (defaults = the measured best; scripts/variant_probe.py builds and times the alternatives)
+#ifndef IDK_NODE_V8
+#define IDK_NODE_V8 1        // sibling pair = 2 x 256-bit loads (LDG.E.256, new on sm_100) instead of 4 x 128-bit
+#endif
+#ifndef IDK_TRI_STRIDE
+#define IDK_TRI_STRIDE 4     // float4s per device-private triangle record: 3 = packed 48 B, 4 = 64 B (one 128-B line, 2 x LDG.E.256)
+#endif
+#ifndef IDK_REG_STACK
+#define IDK_REG_STACK 0      // k_traverse2: top N entries of the traversal stack live in registers (0 = all in shared memory)
+#endif
+
+#ifndef IDK_STAGED_FETCH
+#define IDK_STAGED_FETCH 0   // k_traverse2: rays are prefetched into shared memory one batch ahead (cp.async) instead of fetched in the SETUP round
+#endif
+#ifndef IDK_FAST_VOTE
+#define IDK_FAST_VOTE 0      // k_traverse2: one ballot instead of four when (nearly) every lane is in the BOX phase
+#endif
+#ifndef IDK_LEAF_LOOP
+#define IDK_LEAF_LOOP 0      // k_traverse2: a LEAF round tests a lane's whole pending range instead of one triangle
+#endif
+
+// One GpuBlasNode sibling pair (64 bytes, children are adjacent: BLAS.cs:16-22) / two adjacent GpuTlasNodes.
+struct NodePair { float4 lA, lB, rA, rB; };
+
+__device__ __forceinline__ void ldg256(const void* p, float4& a, float4& b) {   // p 32-byte aligned, read-only data
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(p));
+}
+
+__device__ __forceinline__ NodePair ldg_pair(const float4* np) {
+    NodePair r;
+#if IDK_NODE_V8
+    ldg256(np, r.lA, r.lB);
+    ldg256(np + 2, r.rA, r.rB);
+#else
+    r.lA = ldg4(np); r.lB = ldg4(np + 1); r.rA = ldg4(np + 2); r.rB = ldg4(np + 3);
+#endif
+    return r;
+}
+
+// Device-private triangle record i: (p0.xyz,e1.x) (e1.yz,e2.xy) (e2.z,n.xyz) [pad]
+__device__ __forceinline__ void ldg_tri(const float4* triRec, size_t i, float4& a, float4& b, float4& c) {
+    const float4* tr = triRec + IDK_TRI_STRIDE * i;
+#if IDK_TRI_STRIDE == 4 && IDK_NODE_V8
+    float4 pad;
+    ldg256(tr, a, b);
+    ldg256(tr + 2, c, pad);
+#else
+    a = ldg4(tr); b = ldg4(tr + 1); c = ldg4(tr + 2);
+#endif
+}

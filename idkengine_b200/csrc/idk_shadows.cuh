@@ -15,8 +15,8 @@ __device__ __forceinline__ bool intersect_blas_any(const DeviceScene& sc, const 
     }
     uint32_t sp = 0, top = 2;
     while (true) {
-        const float4* np = nodes + 2 * (size_t)top;
-        const float4 lA = ldg4(np), lB = ldg4(np + 1), rA = ldg4(np + 2), rB = ldg4(np + 3);
+        const NodePair pr = ldg_pair(nodes + 2 * (size_t)top);
+        const float4 lA = pr.lA, lB = pr.lB, rA = pr.rA, rB = pr.rB;
         const int lChild = __float_as_int(lA.w), lCount = __float_as_int(lB.w);
         const int rChild = __float_as_int(rA.w), rCount = __float_as_int(rB.w);
         const bool hitLeft = ray_box(lo, inv, lA, lB, tMinLeft) && tMinLeft <= hit.t;
@@ -26,8 +26,8 @@ __device__ __forceinline__ bool intersect_blas_any(const DeviceScene& sc, const 
             uint32_t first = (intersectLeft ? (uint32_t)lChild : (uint32_t)rChild) + triOffset;
             const uint32_t end = (!intersectRight ? (uint32_t)(lChild + lCount) : (uint32_t)(rChild + rCount)) + triOffset;
             for (uint32_t i = first; i < end; i++) {
-                const float4* tr = sc.triRec + 3 * (size_t)i;
-                const float4 a = ldg4(tr), b = ldg4(tr + 1), c = ldg4(tr + 2);
+                float4 a, b, c;
+                ldg_tri(sc.triRec, i, a, b, c);
                 float bx, by, t;
                 if (ray_triangle(lo, ld, mk3(a.x, a.y, a.z), mk3(a.w, b.x, b.y), mk3(b.z, b.w, c.x), mk3(c.y, c.z, c.w), bx, by, t) && t < hit.t) {
                     hit.tri = i; hit.bx = bx; hit.by = by; hit.t = t;

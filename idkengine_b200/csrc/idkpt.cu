@@ -18,7 +18,7 @@
 #include "idk_post.cuh"
 #include "idk_textures_host.h"
 
-#define IDKPT_ABI_VERSION 2u   // 2: IdkPtSceneDesc gained Textures / TextureCount
+#define IDKPT_ABI_VERSION 3u   // 2: IdkPtSceneDesc gained Textures / TextureCount; 3: IdkPtStats gained CompactMs / AccumulateMs, host-buffer registration
 
 static thread_local std::string g_createError;
 
@@ -100,7 +100,8 @@ struct IdkPtCtx {
     int traverseBlocksLane = 0, traverse1BlocksLane = 0;   // grids of the asynchronous path: the resident-block budget split between the lanes
     int traverseVariant = 3;       // 1 = k_traverse (one ray per lane, reference loop), 2 = k_traverse2 (phase-scheduled warps),
                                    // 3 = k_traverse for the coherent primary rays, k_traverse2 for every bounce (default)
-    TraverseTuning tune = {12, 4};   // swept on B200 (profiles/r01b_tuning.txt)
+    TraverseTuning tune = {12, 4, 0, 6};   // swept on B200 (profiles/r01b_tuning.txt); packRays is set per launch
+    int packAsync = 1;               // IDKPT_PACK_ASYNC: asynchronous (pipelined) launches pack 32 rays per warp instead of spreading few rays over all warps
     size_t stackBytes = 0;
     size_t traverse2Smem = 0;      // treelet + stacks
     int treeletNodes = 0;
@@ -181,27 +182,35 @@ static int configure_launches(IdkPtCtx* ctx) {
     CK(cudaFuncSetAttribute(k_trace_rays, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_trace_rays_any, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
     CK(cudaFuncSetAttribute(k_shadows_ray_traced, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->stackBytes));
-    ctx->traverse2Smem = ctx->stackBytes + (size_t)ctx->treeletNodes * 32;
-    CK(cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
-    CK(cudaFuncSetAttribute(k_traverse2<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
-    CK(cudaFuncSetAttribute(k_traverse2<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
-    CK(cudaFuncSetAttribute(k_traverse2<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    ctx->traverse2Smem = (size_t)stackSize * IDK_T2_BLOCK * sizeof(uint32_t) + (size_t)ctx->treeletNodes * 32 + (IDK_STAGED_FETCH ? IDK_STAGE_BYTES : 0);
+    if (const char* v = getenv("IDKPT_EXTRA_SMEM")) ctx->traverse2Smem += (size_t)std::max(0, atoi(v));   // experiment: L1 capacity sensitivity
+    CK(cudaFuncSetAttribute(k_traverse2<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    CK(cudaFuncSetAttribute(k_traverse2<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    CK(cudaFuncSetAttribute(k_traverse2<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    CK(cudaFuncSetAttribute(k_traverse2<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    CK(cudaFuncSetAttribute(k_traverse2<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
+    CK(cudaFuncSetAttribute(k_traverse2<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ctx->traverse2Smem));
     int n = 0;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
     ctx->traverse1Blocks = std::max(1, n) * ctx->smCount;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, IDK_BLOCK, ctx->stackBytes));
     ctx->traverse1BlocksStats = std::max(1, n) * ctx->smCount;
-    if (ctx->traverseVariant == 1 || ctx->sc.useTlas) {
+    if (ctx->traverseVariant == 1) {
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<false>, IDK_BLOCK, ctx->stackBytes));
         ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
         CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse<true>, IDK_BLOCK, ctx->stackBytes));
         ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
-    } else {
-        if (ctx->treeletNodes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false, true>, IDK_BLOCK, ctx->traverse2Smem));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false, false>, IDK_BLOCK, ctx->traverse2Smem));
+    } else if (ctx->sc.useTlas) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false, false, true>, IDK_T2_BLOCK, ctx->traverse2Smem));
         ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
-        if (ctx->treeletNodes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true, true>, IDK_BLOCK, ctx->traverse2Smem));
-        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true, false>, IDK_BLOCK, ctx->traverse2Smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true, false, true>, IDK_T2_BLOCK, ctx->traverse2Smem));
+        ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
+    } else {
+        if (ctx->treeletNodes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false, true, false>, IDK_T2_BLOCK, ctx->traverse2Smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<false, false, false>, IDK_T2_BLOCK, ctx->traverse2Smem));
+        ctx->traverseBlocks = std::max(1, n) * ctx->smCount;
+        if (ctx->treeletNodes) CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true, true, false>, IDK_T2_BLOCK, ctx->traverse2Smem));
+        else CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_traverse2<true, false, false>, IDK_T2_BLOCK, ctx->traverse2Smem));
         ctx->traverseBlocksStats = std::max(1, n) * ctx->smCount;
     }
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_trace_rays, IDK_BLOCK, ctx->stackBytes));
@@ -233,8 +242,8 @@ static int configure_launches(IdkPtCtx* ctx) {
         if (pct >= 0) {
             cudaFuncSetAttribute(k_traverse<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_traverse<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(k_traverse2<false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
-            cudaFuncSetAttribute(k_traverse2<true, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_traverse2<false, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
+            cudaFuncSetAttribute(k_traverse2<true, false, false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_shade<false>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_shade<true>, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
             cudaFuncSetAttribute(k_compact, cudaFuncAttributePreferredSharedMemoryCarveout, pct);
@@ -495,7 +504,7 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, ci->Device) != cudaSuccess) return fail(nullptr, IDKPT_ERR_CUDA, "idkpt_create: cudaGetDeviceProperties failed");
     if (prop.major < 10) {
-        char buf[256];
+        char buf[512];
         snprintf(buf, sizeof(buf), "idkpt_create: device '%s' is sm_%d%d; libidkpt is built for sm_100a only", prop.name, prop.major, prop.minor);
         return fail(nullptr, IDKPT_ERR_NO_DEVICE, buf);
     }
@@ -515,6 +524,8 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
     if (const char* v = getenv("IDKPT_TRAVERSE_VARIANT")) ctx->traverseVariant = std::max(1, std::min(3, atoi(v)));
     if (const char* v = getenv("IDKPT_TUNE_SETUP")) ctx->tune.setupThreshold = std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("IDKPT_TUNE_LEAF")) ctx->tune.leafThreshold = std::max(1, std::min(32, atoi(v)));
+    if (const char* v = getenv("IDKPT_TUNE_SETUP_STAGED")) ctx->tune.setupThresholdStaged = std::max(1, std::min(32, atoi(v)));
+    if (const char* v = getenv("IDKPT_PACK_ASYNC")) ctx->packAsync = atoi(v) != 0;
     if (const int fl = (ci->Flags >> 8) & 15) ctx->laneCount = std::min(IDK_MAX_LANES, fl);   // IDKPT_CREATE_LANES(n)
     if (const char* v = getenv("IDKPT_LANES")) ctx->laneCount = std::max(1, std::min(IDK_MAX_LANES, atoi(v)));
     if (const char* v = getenv("IDKPT_DEBUG_EPOCH_START")) ctx->epochStart = (uint32_t)strtoul(v, nullptr, 0) & IDK_EPOCH_MASK;
@@ -612,7 +623,7 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
     int rc;
     // nodes and triangle records share one allocation ("bvh"): [nodes | triRec], so that one L2 access-policy window covers both
     const size_t nodeBytes = ((s->BlasNodeCount * sizeof(GpuBlasNode)) + 255) & ~(size_t)255;
-    const size_t triRecBytes = std::max<size_t>(s->BlasTriangleCount, 1) * 48;
+    const size_t triRecBytes = std::max<size_t>(s->BlasTriangleCount, 1) * (16 * IDK_TRI_STRIDE);
     CK(ensure(ctx->nodes, nodeBytes + triRecBytes));
     ctx->treeletNodes = 0;
     std::vector<GpuBlasNode> relaid;
@@ -886,7 +897,19 @@ IDKPT_API int idkpt_stream_handle(IdkPtCtx* ctx, void** stream) {
 IDKPT_API int idkpt_sync(IdkPtCtx* ctx) {
     if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
     CK(cudaSetDevice(ctx->device));
-    return check_device_errors(ctx, drain(ctx), "idkpt_sync");
+    int rc = check_device_errors(ctx, drain(ctx), "idkpt_sync");
+#if IDK_PHASE_STATS
+    if (rc == IDKPT_OK && ctx->counters.p) {   // instrumented build: phase statistics of everything since the last dump (asynchronous path included)
+        TraceCounters tc;
+        CK(cudaMemcpy(&tc, ctx->counters.p, sizeof(tc), cudaMemcpyDeviceToHost));
+        CK(cudaMemset(ctx->counters.p, 0, sizeof(tc)));
+        const double bs = 32.0 * (double)tc.phaseRounds[1];
+        fprintf(stderr, "[idkpt phase stats @sync] rounds SETUP %llu BOX %llu LEAF %llu | lanes/round SETUP %.1f BOX %.1f LEAF %.1f | BOX lane slots: active %.1f%% wait-SETUP %.1f%% wait-LEAF %.1f%% exited %.1f%%\n",
+                tc.phaseRounds[0], tc.phaseRounds[1], tc.phaseRounds[2], (double)tc.phaseLanes[0] / std::max(1ull, tc.phaseRounds[0]), (double)tc.phaseLanes[1] / std::max(1ull, tc.phaseRounds[1]),
+                (double)tc.phaseLanes[2] / std::max(1ull, tc.phaseRounds[2]), 100.0 * tc.phaseLanes[1] / std::max(1.0, bs), 100.0 * tc.boxIdle[0] / std::max(1.0, bs), 100.0 * tc.boxIdle[1] / std::max(1.0, bs), 100.0 * tc.boxIdle[2] / std::max(1.0, bs));
+    }
+#endif
+    return rc;
 }
 
 IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const IdkPtSettings* st, IdkPtStats* stats) {
@@ -990,17 +1013,22 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             ta.traceLights = st->Gpu.DoTraceLights;
             ta.bounce = j;
             e0 = ev.begin();
-            if (ctx->traverseVariant == 1 || ctx->sc.useTlas || (ctx->traverseVariant == 3 && first)) {
+            if (ctx->traverseVariant == 1 || (ctx->traverseVariant == 3 && first)) {
                 if (wantStats) k_traverse<true><<<ctx->traverse1BlocksStats, IDK_BLOCK, ctx->stackBytes, ls>>>(ta);
                 else k_traverse<false><<<async ? ctx->traverse1BlocksLane : ctx->traverse1Blocks, IDK_BLOCK, ctx->stackBytes, ls>>>(ta);
             } else {
                 const int tb = async ? ctx->traverseBlocksLane : ctx->traverseBlocks;
-                if (ctx->treeletNodes) {
-                    if (wantStats) k_traverse2<true, true><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->traverse2Smem, ls>>>(ta, ctx->tune);
-                    else k_traverse2<false, true><<<tb, IDK_BLOCK, ctx->traverse2Smem, ls>>>(ta, ctx->tune);
+                TraverseTuning tune = ctx->tune;
+                tune.packRays = (async && ctx->packAsync) ? 1 : 0;
+                if (ctx->sc.useTlas) {       // the TLAS walk is a fourth phase of the production kernel (BVHIntersect.glsl:205-272)
+                    if (wantStats) k_traverse2<true, false, true><<<ctx->traverseBlocksStats, IDK_T2_BLOCK, ctx->traverse2Smem, ls>>>(ta, tune);
+                    else k_traverse2<false, false, true><<<tb, IDK_T2_BLOCK, ctx->traverse2Smem, ls>>>(ta, tune);
+                } else if (ctx->treeletNodes) {
+                    if (wantStats) k_traverse2<true, true, false><<<ctx->traverseBlocksStats, IDK_T2_BLOCK, ctx->traverse2Smem, ls>>>(ta, tune);
+                    else k_traverse2<false, true, false><<<tb, IDK_T2_BLOCK, ctx->traverse2Smem, ls>>>(ta, tune);
                 } else {
-                    if (wantStats) k_traverse2<true, false><<<ctx->traverseBlocksStats, IDK_BLOCK, ctx->traverse2Smem, ls>>>(ta, ctx->tune);
-                    else k_traverse2<false, false><<<tb, IDK_BLOCK, ctx->traverse2Smem, ls>>>(ta, ctx->tune);
+                    if (wantStats) k_traverse2<true, false, false><<<ctx->traverseBlocksStats, IDK_T2_BLOCK, ctx->traverse2Smem, ls>>>(ta, tune);
+                    else k_traverse2<false, false, false><<<tb, IDK_T2_BLOCK, ctx->traverse2Smem, ls>>>(ta, tune);
                 }
             }
             ev.end(e0, 0, j);
@@ -1045,7 +1073,9 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                     ln.epoch = 0;
                 }
                 ca.epoch = ++ln.epoch;
+                const size_t ec = ev.begin();
                 k_compact<<<ctx->compactBlocks, IDK_BLOCK, 0, ls>>>(ca);
+                ev.end(ec, 5);
                 launches++;
             }
             ev.end(e0, 1, j);
@@ -1089,6 +1119,7 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             launches++;
         }
         ev.end(e0, 3);
+        ev.end(e0, 6);
         if (stats) CK(cudaMemcpyAsync((uint32_t*)countLog.p + (size_t)s * (IDKPT_MAX_RAY_DEPTH + 1), counts,
                                       (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t), cudaMemcpyDeviceToDevice, ctx->stream));
         ctx->accumulatedSamples++;   // PathTracer.cs:269
@@ -1118,6 +1149,12 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             stats->TriangleTests = tc.tris;
             stats->InstanceVisits = tc.instances;
             stats->Hits = tc.hits;
+#if IDK_PHASE_STATS
+            fprintf(stderr, "[idkpt phase stats] SETUP rounds %llu lanes %llu | BOX rounds %llu lanes %llu | LEAF rounds %llu lanes %llu\n", tc.phaseRounds[0], tc.phaseLanes[0],
+                    tc.phaseRounds[1], tc.phaseLanes[1], tc.phaseRounds[2], tc.phaseLanes[2]);
+            fprintf(stderr, "[idkpt phase stats] during BOX rounds, idle lanes: waiting SETUP %llu, waiting LEAF %llu, exited %llu\n", tc.boxIdle[0], tc.boxIdle[1], tc.boxIdle[2]);
+            { double mx = 0; for (int j = 0; j < st->RayDepth; j++) mx += tc.maxSteps[j]; fprintf(stderr, "[idkpt phase stats] sum over bounces of the longest ray: %.0f steps\n", mx); }
+#endif
             for (int j = 0; j < IDKPT_MAX_RAY_DEPTH; j++) stats->BounceMaxSteps[j] = tc.maxSteps[j];
         }
         for (const EventPool::Span& sp : ev.spans) {
@@ -1128,6 +1165,8 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                 case 1: stats->ShadeMs += ms; if (sp.bounce >= 0) stats->BounceShadeMs[sp.bounce] += ms; break;
                 case 2: stats->SortMs += ms; break;
                 case 3: stats->OtherMs += ms; break;
+                case 5: stats->CompactMs += ms; break;
+                case 6: stats->AccumulateMs += ms; break;
                 default: stats->TotalMs = ms; break;
             }
         }
@@ -1200,14 +1239,21 @@ IDKPT_API int idkpt_present_async(IdkPtCtx* ctx, IdkPtImage which, void* dstHost
     CK(cudaMemcpyAsync(ctx->presentSnap.p, ctx->images[which].p, n, cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaEventRecord(ctx->snapDone, ctx->stream));
     CK(cudaStreamWaitEvent(ctx->copyStream, ctx->snapDone, 0));
+    // The tile's rows are stored compactly, stripe after stripe; in the full-frame host layout its stripes are tileCount stripes
+    // apart: ONE strided (2-D) copy moves all complete stripes, a second one the partial last stripe of the image if it is ours.
+    // With a host frame shared by all ranks (idkpt_register_host_buffer on the same mapping in every process) each GPU
+    // delivers its own 1/N of the frame over its own PCIe link -- no rank has to download the whole gathered image.
     const size_t rowBytes = (size_t)ctx->width * 16;
-    size_t i = 0;
-    while (i < ctx->rows.size()) {
-        size_t j = i;
-        while (j + 1 < ctx->rows.size() && ctx->rows[j + 1] == ctx->rows[j] + 1) j++;
-        CK(cudaMemcpyAsync((char*)dstHost + (size_t)ctx->rows[i] * rowBytes, (char*)ctx->presentSnap.p + i * rowBytes, (j - i + 1) * rowBytes,
-                           cudaMemcpyDeviceToHost, ctx->copyStream));
-        i = j + 1;
+    if (!ctx->rows.empty()) {
+        const size_t stripeBytes = (size_t)ctx->stripeH * rowBytes;
+        const size_t fullStripes = ctx->rows.size() / (size_t)ctx->stripeH, tailRows = ctx->rows.size() % (size_t)ctx->stripeH;
+        char* h0 = (char*)dstHost + (size_t)ctx->rows[0] * rowBytes;
+        if (fullStripes)
+            CK(cudaMemcpy2DAsync(h0, stripeBytes * (size_t)ctx->tileCount, ctx->presentSnap.p, stripeBytes, stripeBytes, fullStripes,
+                                 cudaMemcpyDeviceToHost, ctx->copyStream));
+        if (tailRows)
+            CK(cudaMemcpyAsync((char*)dstHost + (size_t)ctx->rows[fullStripes * ctx->stripeH] * rowBytes, (char*)ctx->presentSnap.p + fullStripes * stripeBytes,
+                               tailRows * rowBytes, cudaMemcpyDeviceToHost, ctx->copyStream));
     }
     CK(cudaEventRecord(ctx->copyDone, ctx->copyStream));
     ctx->copyPending = true;
@@ -1221,6 +1267,23 @@ IDKPT_API int idkpt_present_wait(IdkPtCtx* ctx) {
         CK(cudaEventSynchronize(ctx->copyDone));
         ctx->copyPending = false;
     }
+    return IDKPT_OK;
+}
+
+// Page-lock a host buffer the engine owns (e.g. the POSIX shared-memory frame all ranks present into) so that
+// idkpt_present_async's copies are truly asynchronous. The C# host has no CUDA runtime of its own to call cudaHostRegister.
+IDKPT_API int idkpt_register_host_buffer(IdkPtCtx* ctx, void* hostPtr, uint64_t bytes) {
+    if (!ctx || !hostPtr || !bytes) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_register_host_buffer: null argument");
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaHostRegister(hostPtr, bytes, cudaHostRegisterPortable));
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_unregister_host_buffer(IdkPtCtx* ctx, void* hostPtr) {
+    if (!ctx || !hostPtr) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_unregister_host_buffer: null argument");
+    CK(cudaSetDevice(ctx->device));
+    if (ctx->copyPending) { CK(cudaEventSynchronize(ctx->copyDone)); ctx->copyPending = false; }   // a transfer may still target it
+    CK(cudaHostUnregister(hostPtr));
     return IDKPT_OK;
 }
 

@@ -194,6 +194,13 @@ class PathTracer:
     def PresentWait(self):
         self._check(self._lib.idkpt_present_wait(self._ctx), "idkpt_present_wait")
 
+    def RegisterHostBuffer(self, host_ptr, nbytes):
+        """Page-lock an engine-owned host buffer (e.g. the shared-memory frame every rank presents its stripes into)."""
+        self._check(self._lib.idkpt_register_host_buffer(self._ctx, host_ptr, nbytes), "idkpt_register_host_buffer")
+
+    def UnregisterHostBuffer(self, host_ptr):
+        self._check(self._lib.idkpt_unregister_host_buffer(self._ctx, host_ptr), "idkpt_unregister_host_buffer")
+
     def EnablePeerGather(self, rank, world, exchange):
         """Multi-GPU: fuse the tile all-gather into Compute() over NVLink peer memory. `exchange(bytes) -> list[bytes]`
         must return every rank's blob in rank order (e.g. torch.distributed.all_gather_object)."""

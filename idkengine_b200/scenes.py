@@ -309,6 +309,42 @@ def multi_blas(threads=None):
 
 
 
+def instance_grid(n=3, threads=None):
+    """n^3 small models (spheres, boxes, cylinders; rotated / non-uniformly scaled instances) over a floor: a TLAS with
+    2*(n^3+1)-1 nodes whose walk (BVHIntersect.glsl:205-272) is several levels deep, unlike multi_blas' three instances."""
+    models = []
+    meshes, mats = _materials([dict(color=(0.75, 0.75, 0.7))])
+    a = _Assembler()
+    a.add(quad([-6, 0, -6], [-6, 0, 6], [6, 0, 6], [6, 0, -6]), 0)
+    models.append(a.model(meshes, mats, name="floor"))
+    k = 0
+    for ix in range(n):
+        for iy in range(n):
+            for iz in range(n):
+                col = (0.25 + 0.25 * ix, 0.3 + 0.2 * iy, 0.35 + 0.2 * iz)
+                spec = dict(color=col, metallic=0.5 if k % 3 == 0 else 0.0, roughness=0.2 + 0.1 * (k % 5))
+                if k % 7 == 3:
+                    spec = dict(color=(1.0, 0.9, 0.7), emissive=(6.0, 5.0, 3.0))
+                m, t = _materials([spec])
+                b = _Assembler()
+                kind = k % 3
+                if kind == 0:
+                    b.add(uv_sphere([0, 0, 0], 0.45, 10, 14), 0)
+                elif kind == 1:
+                    b.add(box([-0.4, -0.4, -0.4], [0.4, 0.4, 0.4]), 0)
+                else:
+                    b.add(cylinder([0, -0.4, 0], 0.3, 0.8, 12, 3), 0)
+                pos = (-2.4 + 2.4 * ix + 0.3 * iy, 0.7 + 1.5 * iy, -2.4 + 2.4 * iz - 0.2 * ix)
+                scale = (0.8 + 0.15 * (k % 4), 0.9 + 0.2 * (k % 3), 1.0 + 0.1 * (k % 2))
+                models.append(b.model(m, t, model_matrix=trs_matrix(scale, 17.0 * k, pos), name=f"obj{k}"))
+                k += 1
+    scene = Scene().add(*models, threads=threads)
+    scene.add_light((0.0, 6.0, 0.0), (40.0, 38.0, 34.0), 0.4)
+    scene.build_tlas()
+    cam = dict(position=(0.5, 3.2, 8.5), view_dir=(-0.05, -0.28, -1.0), fov_y_deg=55.0)
+    return scene, cam
+
+
 # --------------------------------------------------------------------------- textured room (material textures)
 def _checker(n, cells, a, b, alpha_a=255, alpha_b=255, seed=0):
     rng = np.random.default_rng(seed)

@@ -146,6 +146,8 @@ typedef struct IdkPtStats {
     float    BounceTraverseMs[IDKPT_MAX_RAY_DEPTH];   /* per bounce, summed over samples */
     float    BounceShadeMs[IDKPT_MAX_RAY_DEPTH];      /* shade + compaction */
     uint32_t BounceMaxSteps[IDKPT_MAX_RAY_DEPTH];     /* longest ray (node-pair fetches) per bounce (valid if CollectStats) */
+    float    CompactMs;                          /* ABI 3: the ordered compaction launches alone (also contained in ShadeMs / BounceShadeMs) */
+    float    AccumulateMs;                       /* ABI 3: FinalDraw (+ fused peer scatter and arrival wait) alone (also contained in OtherMs) */
 } IdkPtStats;
 
 typedef enum IdkPtImage {
@@ -217,6 +219,11 @@ IDKPT_API int idkpt_write_result(IdkPtCtx* ctx, IdkPtImage which, const void* sr
  * most recent transfer has landed. The GL-free analogue of handing Result to the presenter each frame. */
 IDKPT_API int idkpt_present_async(IdkPtCtx* ctx, IdkPtImage which, void* dst_rgba32f_host, uint64_t bytes);
 IDKPT_API int idkpt_present_wait(IdkPtCtx* ctx);
+/* Page-lock (cudaHostRegister) a host buffer owned by the engine so that idkpt_present_async into it is asynchronous, e.g.
+ * ONE frame in POSIX shared memory registered by every rank: each rank's idkpt_present_async(IDKPT_IMAGE_RESULT) then
+ * delivers its own stripes to their final position over its own PCIe link (multi-GPU presentation without a root copy). */
+IDKPT_API int idkpt_register_host_buffer(IdkPtCtx* ctx, void* host_ptr, uint64_t bytes);
+IDKPT_API int idkpt_unregister_host_buffer(IdkPtCtx* ctx, void* host_ptr);
 
 /* Multi-GPU tile gather over NVLink peer memory (no NCCL in the data path). Every rank calls idkpt_gather_export
  * (allocates a double-buffered full-size image + arrival flags and returns 4 CUDA IPC handles = 256 bytes), the ranks

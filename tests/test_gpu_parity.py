@@ -168,6 +168,55 @@ def test_tlas_traversal(multi_blas):
     assert_same(*run_both(scene, cam, 128, 96, s, calls=2))
 
 
+def test_tlas_walk_in_the_production_kernel():
+    """28 instances -> 55 TLAS nodes. The phase-scheduled kernel (TLAS = 4th phase, default) and the one-ray-per-lane kernel
+    (IDKPT_TRAVERSE_VARIANT=1) both equal the oracle: images, wavefront state and S/T/I counters; so do 4 samples in flight."""
+    import os
+    scene, cam = scenes.instance_grid(3, threads=1)
+    assert scene.use_tlas == 1 and len(scene.tlas_nodes) == 2 * len(scene.blas_instances) - 1 == 55
+    s = capi.default_settings()
+    s.RayDepth = 6
+    s.Gpu.DoTraceLights = 1
+    w, h = 256, 160
+    g, o = run_both(scene, cam, w, h, s, calls=2)
+    assert_same(g, o)
+    assert g["stats"][0].InstanceVisits > g["stats"][0].Rays // 2    # the walk reaches BLASes for most rays (28 instances, culled by the TLAS)
+    os.environ["IDKPT_TRAVERSE_VARIANT"] = "1"
+    try:
+        g1, _ = run_both(scene, cam, w, h, s, calls=2)
+    finally:
+        del os.environ["IDKPT_TRAVERSE_VARIANT"]
+    assert_same(g1, o)
+    frame = scenes.camera_frame(cam, w, h)
+    with PathTracer(w, h, s, lanes=4) as pt:
+        pt.SetScene(scene); pt.SetSky((0.6, 0.7, 0.9)); pt.SetFrame(frame)
+        pt.ComputeAsync(); pt.ComputeAsync()
+        pt.Sync()
+        assert feq(pt.Result, o["result"])
+
+
+def test_compaction_epoch_wraps_without_hanging(cornell):
+    """The decoupled look-back's status words carry a 30-bit epoch; a long-running renderer wraps it (advisor finding,
+    round 1: the kernel used to spin forever). IDKPT_DEBUG_EPOCH_START puts a fresh context 6 compactions before the wrap."""
+    import os
+    scene, cam = cornell
+    s = capi.default_settings()
+    s.RayDepth = 6
+    os.environ["IDKPT_DEBUG_EPOCH_START"] = str(0x3FFFFFFF - 6)
+    try:
+        g, o = run_both(scene, cam, 160, 120, s, calls=4)      # 20 compactions on lane 0: crosses the wrap
+        assert_same(g, o)
+        frame = scenes.camera_frame(cam, 160, 120)
+        with PathTracer(160, 120, s, lanes=3) as pt:            # every lane wraps on its own stream
+            pt.SetScene(scene); pt.SetSky((0.6, 0.7, 0.9)); pt.SetFrame(frame)
+            for _ in range(4):
+                pt.ComputeAsync()
+            pt.Sync()
+            assert feq(pt.Result, o["result"])
+    finally:
+        del os.environ["IDKPT_DEBUG_EPOCH_START"]
+
+
 def test_path_trace_debug_traversal(cornell):
     scene, cam = cornell
     s = capi.default_settings()
