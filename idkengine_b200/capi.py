@@ -24,11 +24,14 @@ class IdkPtCreateInfo(ctypes.Structure):
 
 
 IDKPT_TEX_RGBA8_UNORM, IDKPT_TEX_RGBA8_SRGB = 0, 1
+IDKPT_TEX_BC7_UNORM, IDKPT_TEX_BC7_SRGB, IDKPT_TEX_BC5_RG_UNORM, IDKPT_TEX_BC4_R_UNORM = 2, 3, 4, 5
+IDKPT_TEX_RG32F, IDKPT_TEX_R32F, IDKPT_TEX_RGBA32F = 6, 7, 8
+IDKPT_TEX_FLAG_R_FROM_B = 1
 GL_REPEAT, GL_CLAMP_TO_EDGE, GL_MIRRORED_REPEAT = 10497, 33071, 33648
 
 
 class IdkPtTextureDesc(ctypes.Structure):
-    _fields_ = [("Pixels", c_vp), ("Width", c_i32), ("Height", c_i32), ("Format", c_i32), ("WrapS", c_i32), ("WrapT", c_i32), ("_pad0", c_i32)]
+    _fields_ = [("Pixels", c_vp), ("Width", c_i32), ("Height", c_i32), ("Format", c_i32), ("WrapS", c_i32), ("WrapT", c_i32), ("Flags", c_i32)]
 
 
 class IdkPtSceneDesc(ctypes.Structure):
@@ -153,14 +156,22 @@ def scene_desc(scene):
 
 
 def texture_descs(textures):
-    """IdkPtTextureDesc array for a list of dict(pixels [H, W, 4] uint8, srgb, wrap_s, wrap_t). Returns (array, keepalive)."""
+    """IdkPtTextureDesc array for a list of texture dicts (host.Scene.textures). Returns (array, keepalive).
+      uncompressed RGBA8:  dict(pixels [H, W, 4] uint8, srgb, wrap_s, wrap_t)
+      any other format:    dict(format=IDKPT_TEX_*, width, height, data=<level-0 bytes: block stream or float texels>, wrap_s, wrap_t, flags)"""
     keep = []
     arr = (IdkPtTextureDesc * max(len(textures), 1))()
     for i, t in enumerate(textures):
+        if "format" in t:
+            data = np.ascontiguousarray(t["data"])
+            keep.append(data)
+            arr[i] = IdkPtTextureDesc(data.ctypes.data, int(t["width"]), int(t["height"]), int(t["format"]),
+                                      t.get("wrap_s", GL_REPEAT), t.get("wrap_t", GL_REPEAT), int(t.get("flags", 0)))
+            continue
         px = np.ascontiguousarray(t["pixels"], np.uint8)
         keep.append(px)
         arr[i] = IdkPtTextureDesc(px.ctypes.data, px.shape[1], px.shape[0], IDKPT_TEX_RGBA8_SRGB if t.get("srgb") else IDKPT_TEX_RGBA8_UNORM,
-                                  t.get("wrap_s", GL_REPEAT), t.get("wrap_t", GL_REPEAT), 0)
+                                  t.get("wrap_s", GL_REPEAT), t.get("wrap_t", GL_REPEAT), int(t.get("flags", 0)))
     keep.append(arr)
     return arr, keep
 

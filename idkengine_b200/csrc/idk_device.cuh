@@ -85,11 +85,11 @@ __device__ __forceinline__ float det_log2(float x) {
 
 // One 2-D RGBA8 texture, base level only: compute shaders sample lod 0 (Surface.glsl:57-60).
 struct TexRec {
-    const uchar4* px;
+    const void* px;               // decoded level 0: uchar4 (kind 0), float2 (1), float (2) or float4 (3) texels
     int w, h;
     int wrapS, wrapT;             // GL enums: 10497 REPEAT, 33071 CLAMP_TO_EDGE, 33648 MIRRORED_REPEAT
-    int srgb;                     // rgb decoded through srgbLut before filtering (GL_SRGB8_ALPHA8)
-    int pad;
+    int srgb;                     // rgb decoded through srgbLut before filtering (GL_SRGB8_ALPHA8 / BC7 sRGB)
+    int kind;                     // bits 0-7: texel storage kind, bit 8: R channel reads B (IDKPT_TEX_FLAG_R_FROM_B)
 };
 
 // ---- material textures: texture(sampler2D, uv) at lod 0 = bilinear on the base level, evaluated explicitly in fp32
@@ -101,9 +101,23 @@ __device__ __forceinline__ int tex_wrap(int i, int n, int mode) {
     return m < 0 ? m + n : m;
 }
 __device__ __forceinline__ float4 tex_fetch(const TexRec& t, const float* lut, int x, int y) {
-    const uchar4 c = __ldg(t.px + (size_t)y * t.w + x);
-    if (t.srgb) return make_float4(__ldg(lut + c.x), __ldg(lut + c.y), __ldg(lut + c.z), (float)c.w / 255.0f);
-    return make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+    const size_t i = (size_t)y * t.w + x;
+    const int kind = t.kind & 255;
+    float4 r;
+    if (kind == 0) {
+        const uchar4 c = __ldg((const uchar4*)t.px + i);
+        if (t.srgb) r = make_float4(__ldg(lut + c.x), __ldg(lut + c.y), __ldg(lut + c.z), (float)c.w / 255.0f);
+        else r = make_float4((float)c.x / 255.0f, (float)c.y / 255.0f, (float)c.z / 255.0f, (float)c.w / 255.0f);
+    } else if (kind == 1) {       // GL returns (R, G, 0, 1) for a two-channel texture
+        const float2 c = __ldg((const float2*)t.px + i);
+        r = make_float4(c.x, c.y, 0.0f, 1.0f);
+    } else if (kind == 2) {
+        r = make_float4(__ldg((const float*)t.px + i), 0.0f, 0.0f, 1.0f);
+    } else {
+        r = __ldg((const float4*)t.px + i);
+    }
+    if (t.kind & 256) r.x = r.z;
+    return r;
 }
 __device__ __forceinline__ float4 tex_lerp(float4 a, float4 b, float t) {
     const float s = 1.0f - t;

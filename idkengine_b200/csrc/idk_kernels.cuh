@@ -1022,8 +1022,11 @@ __device__ __forceinline__ uint32_t status_epoch(unsigned long long sv) { return
 // One thread per alive ray, no block-level cooperation: every warp runs at its own pace (the ordered compaction of
 // the reference's atomic alive list is a separate, uniform-cost pass over 4-byte entries: k_compact).
 // TEX = the scene has material textures (idkpt_set_scene); the untextured instantiation is the north-star path.
+#ifndef IDK_SHADE_MIN_BLOCKS
+#define IDK_SHADE_MIN_BLOCKS 3
+#endif
 template <bool TEX>
-__global__ void __launch_bounds__(IDK_BLOCK, 3) k_shade(ShadeArgs a) {
+__global__ void __launch_bounds__(IDK_BLOCK, IDK_SHADE_MIN_BLOCKS) k_shade(ShadeArgs a) {
     const uint32_t count = *a.count;
     const DeviceScene& sc = a.sc;
     const FrameParams& f = a.f;

@@ -415,14 +415,8 @@ static int upload_textures(IdkPtCtx* ctx, const IdkPtTextureDesc* textures, uint
     tmp.Textures = textures; tmp.TextureCount = count;
     const std::vector<size_t> off = idk_texture_offsets(&tmp);
     CK(ensure(ctx->texPixels, std::max<size_t>(off[count], 16)));
-    std::vector<TexRec> recs(count);
-    for (uint64_t i = 0; i < count; i++) {
-        const IdkPtTextureDesc& t = textures[i];
-        CK(cudaMemcpyAsync((char*)ctx->texPixels.p + off[i], t.Pixels, (size_t)t.Width * t.Height * 4, cudaMemcpyHostToDevice, ctx->stream));
-        recs[i].px = (const uchar4*)((char*)ctx->texPixels.p + off[i]);
-        recs[i].w = t.Width; recs[i].h = t.Height; recs[i].wrapS = t.WrapS; recs[i].wrapT = t.WrapT;
-        recs[i].srgb = t.Format == IDKPT_TEX_RGBA8_SRGB ? 1 : 0; recs[i].pad = 0;
-    }
+    std::vector<TexRec> recs;
+    CK(idk_upload_texture_table(textures, count, off, ctx->texPixels.p, ctx->stream, recs));
     int rc;
     if ((rc = upload(ctx, ctx->texRecs, recs.data(), recs.size() * sizeof(TexRec)))) return rc;
     float lut[256];

@@ -84,6 +84,7 @@ IDKPT_API int idkvx_create(const IdkVxCreateInfo* ci, IdkVxCtx** out) {
     IdkVxCtx* ctx = new IdkVxCtx();
     ctx->device = ci->Device;
     ctx->smCount = prop.multiProcessorCount;
+    cudaFuncSetAttribute(k_vx_mipmap_tiled, cudaFuncAttributeMaxDynamicSharedMemorySize, IDKVX_MIP_TILE_SMEM);
     if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) { delete ctx; return vfail(nullptr, IDKPT_ERR_CUDA, "idkvx_create: stream creation failed"); }
     // Texture.GetMaxMipmapLevel: levels down to 1 texel of the largest extent
     const int mx = std::max(ci->Width, std::max(ci->Height, ci->Depth));
@@ -173,16 +174,10 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
     if ((rc = vupload(ctx, &ctx->dLights, s->Lights, s->LightCount * sizeof(GpuLight)))) return rc;
     {   // material textures (BaseColor / Emissive are the slots the voxeliser's fragment stage uses)
         const std::vector<size_t> off = idk_texture_offsets(s);
-        std::vector<unsigned char> packed(std::max<size_t>(off[s->TextureCount], 16), 0);
-        std::vector<TexRec> recs(std::max<uint64_t>(s->TextureCount, 1));
-        for (uint64_t i = 0; i < s->TextureCount; i++) memcpy(packed.data() + off[i], s->Textures[i].Pixels, (size_t)s->Textures[i].Width * s->Textures[i].Height * 4);
-        if ((rc = vupload(ctx, &ctx->dTexPixels, packed.data(), packed.size()))) return rc;
-        for (uint64_t i = 0; i < s->TextureCount; i++) {
-            const IdkPtTextureDesc& t = s->Textures[i];
-            recs[i].px = (const uchar4*)((const char*)ctx->dTexPixels + off[i]);
-            recs[i].w = t.Width; recs[i].h = t.Height; recs[i].wrapS = t.WrapS; recs[i].wrapT = t.WrapT;
-            recs[i].srgb = t.Format == IDKPT_TEX_RGBA8_SRGB ? 1 : 0; recs[i].pad = 0;
-        }
+        std::vector<TexRec> recs;
+        if (ctx->dTexPixels) { cudaFree(ctx->dTexPixels); ctx->dTexPixels = nullptr; }
+        VCK(cudaMalloc(&ctx->dTexPixels, std::max<size_t>(off[s->TextureCount], 16)));
+        VCK(idk_upload_texture_table(s->Textures, s->TextureCount, off, ctx->dTexPixels, ctx->stream, recs));
         if ((rc = vupload(ctx, &ctx->dTexRecs, recs.data(), recs.size() * sizeof(TexRec)))) return rc;
         float lut[256];
         idk_srgb_lut(lut);
@@ -247,7 +242,16 @@ IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats) {
     for (int l = 1; l < ctx->grid.levels; l++) {
         const size_t n = ctx->levelTexels[l];
         const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->smCount * 16);
-        k_vx_mipmap<<<blocks, 256, 0, ctx->stream>>>(ctx->grid, l);
+        // levels that halve exactly on every axis and are big enough to fill the machine take the shared-memory tiled kernel
+        const VxGridDev& gd = ctx->grid;
+        const bool halves = gd.sx[l - 1] == 2 * gd.sx[l] && gd.sy[l - 1] == 2 * gd.sy[l] && gd.sz[l - 1] == 2 * gd.sz[l];
+        const bool tiledOff = getenv("IDKVX_MIP_TILED") && atoi(getenv("IDKVX_MIP_TILED")) == 0;      // developer knob (cross-check)
+        if (halves && n >= 4096 && !tiledOff) {
+            const int tiles = ((gd.sx[l] + IDKVX_MT_X - 1) / IDKVX_MT_X) * ((gd.sy[l] + IDKVX_MT_Y - 1) / IDKVX_MT_Y) * ((gd.sz[l] + IDKVX_MT_Z - 1) / IDKVX_MT_Z);
+            k_vx_mipmap_tiled<<<std::min(tiles, ctx->smCount * 4), 256, IDKVX_MIP_TILE_SMEM, ctx->stream>>>(ctx->grid, l);
+        } else {
+            k_vx_mipmap<<<blocks, 256, 0, ctx->stream>>>(ctx->grid, l);
+        }
         launches++;
     }
     VCK(cudaEventRecord(ev[3], ctx->stream));

@@ -356,6 +356,13 @@ class Scene:
         self.textures.append(dict(pixels=pixels, srgb=bool(srgb), wrap_s=int(wrap_s), wrap_t=int(wrap_t)))
         return len(self.textures)
 
+    def add_texture_raw(self, fmt, width, height, data, wrap_s=10497, wrap_t=10497, flags=0):
+        """Registers a texture in one of the other IdkPtTextureFormat formats: the level-0 BC7 / BC5 / BC4 block stream of a
+        KTX2 image as the loader hands it to GL (ModelLoader.cs:954-968), or R / RG / RGBA float texels. Returns the handle."""
+        self.textures.append(dict(format=int(fmt), width=int(width), height=int(height), data=np.ascontiguousarray(data),
+                                  wrap_s=int(wrap_s), wrap_t=int(wrap_t), flags=int(flags)))
+        return len(self.textures)
+
     def add_light(self, position, color, radius):
         """LightManager.AddLight (SRC/Render/LightManager.cs) -> GpuLight in UBO 2."""
         l = np.zeros(1, gt.GpuLight)

@@ -135,3 +135,58 @@ class Voxelizer:
         self._check(self._lib.idkvx_cone_trace(self._ctx, frame.ctypes.data, ctypes.byref(settings), depth.ctypes.data, nrg.ctypes.data,
                                                mr.ctypes.data, w, h, ctypes.byref(skyc), out.ctypes.data, ctypes.byref(st)), "idkvx_cone_trace")
         return out, st
+
+
+def camera_rays(frame, width, height):
+    """Pinhole rays through the pixel grid, built like Ray.GetWorldSpaceRay (SRC/Shapes/Ray.cs:30-39) from GpuPerFrameData's
+    InvProjection / InvView with ndc = (x, y) / resolution * 2 - 1 (the shape Gui.Test uses, Gui.cs:1484-1503)."""
+    f = frame[0] if frame.ndim else frame
+    ip = np.asarray(f["InvProjection"], np.float32).reshape(-1)
+    iv = np.asarray(f["InvView"], np.float32).reshape(-1)
+    xs = (np.arange(width, dtype=np.float32) / np.float32(width) * np.float32(2.0) - np.float32(1.0))[None, :]
+    ys = (np.arange(height, dtype=np.float32) / np.float32(height) * np.float32(2.0) - np.float32(1.0))[:, None]
+    vx = xs * ip[0] + ys * ip[4]
+    vy = xs * ip[1] + ys * ip[5]
+    w = np.stack([vx * iv[0] + vy * iv[4] - iv[8], vx * iv[1] + vy * iv[5] - iv[9], vx * iv[2] + vy * iv[6] - iv[10]], -1).astype(np.float32)
+    w /= np.sqrt((w * w).sum(-1, keepdims=True, dtype=np.float32))
+    rays = np.zeros(width * height, gt.IdkPtRay)
+    rays["Origin"] = np.asarray(f["ViewPos"], np.float32).reshape(-1)[:3]
+    rays["TMax"] = np.float32(3.4028235e38)
+    rays["Direction"] = w.reshape(-1, 3)
+    return rays
+
+
+def synth_gbuffer(pt, scene, frame, width, height):
+    """The G-buffer attachments ConeTracer.Compute reads (depth, octahedral normal, metallic/roughness), synthesised from the
+    path tracer's first hit on the GPU (`pt.TraceRays`) for scenes that have no rasteriser behind them."""
+    rays = camera_rays(frame, width, height)
+    hits, _ = pt.TraceRays(rays)
+    hit = hits["TriangleId"] != 0xFFFFFFFF
+    o = rays["Origin"].astype(np.float64)
+    d = rays["Direction"].astype(np.float64)
+    pos = o + d * hits["T"][:, None].astype(np.float64)
+    f = frame[0] if frame.ndim else frame
+    pv = np.asarray(f["ProjView"], np.float64).reshape(4, 4)            # OpenTK rows: clip = [p, 1] @ pv
+    clip = np.concatenate([pos, np.ones((len(pos), 1))], 1) @ pv
+    with np.errstate(all="ignore"):
+        depth = np.where(hit, clip[:, 2] / clip[:, 3], 1.0).astype(np.float32)
+    depth = np.where(hit & (depth >= 1.0), np.float32(0.999999), depth)
+    tri = scene.blas_triangles[np.where(hit, hits["TriangleId"], 0)]
+    P = scene.positions
+
+    def pnt(k):
+        return np.stack([P["x"][tri[k]], P["y"][tri[k]], P["z"][tri[k]]], 1).astype(np.float64)
+    p0, p1, p2 = pnt("X"), pnt("Y"), pnt("Z")
+    n = np.cross(p1 - p0, p2 - p0)
+    inv = scene.mesh_transforms["InvModelMatrix"][hits["MeshTransformId"]][:, :, :3].astype(np.float64)
+    n = np.einsum("nji,nj->ni", inv, n)
+    n /= np.maximum(np.linalg.norm(n, axis=1, keepdims=True), 1e-30)
+    n = np.where((np.sum(n * d, 1) > 0)[:, None], -n, n)
+    m = n / np.sum(np.abs(n), 1, keepdims=True)                        # EncodeUnitVec (Compression.glsl:54-61)
+    wrap = (1.0 - np.abs(m[:, [1, 0]])) * np.where(m[:, :2] < 0, -1.0, 1.0)
+    xy = np.where((m[:, 2] > 0)[:, None], m[:, :2], wrap)
+    nrg = (xy * 0.5 + 0.5).astype(np.float32)
+    mesh = scene.meshes[tri["MeshId"]]
+    mat = scene.materials[mesh["MaterialId"]]
+    mr = np.stack([np.clip(mat["MetallicFactor"] + mesh["SpecularBias"], 0, 1), np.clip(mat["RoughnessFactor"] + mesh["RoughnessBias"], 0, 1)], 1).astype(np.float32)
+    return depth.reshape(height, width), nrg.reshape(height, width, 2), mr.reshape(height, width, 2)

@@ -45,6 +45,10 @@
 #include <cfloat>
 #include <vector>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <atomic>
+#include <functional>
 #include <algorithm>
 #include <chrono>
 
@@ -591,10 +595,22 @@ static const float* SrgbLut() {
     }
     return lut;
 }
+// The oracle samples UNCOMPRESSED texels only (RGBA8 unorm / sRGB, R / RG / RGBA 32F; GL channel defaults (R,G,0,1) for missing
+// channels). Block-compressed textures reach it already decoded by tests/bcn_ref.py, an implementation that shares no code
+// with the CUDA decoders (csrc/idk_bcn.cuh) -- the two are then compared through the rendered images.
 static inline Vec4 TexFetch(const IdkPtTextureDesc& t, int x, int y) {
-    const uint8_t* c = (const uint8_t*)t.Pixels + 4 * ((size_t)y * t.Width + x);
-    if (t.Format == IDKPT_TEX_RGBA8_SRGB) { const float* lut = SrgbLut(); return {lut[c[0]], lut[c[1]], lut[c[2]], (float)c[3] / 255.0f}; }
-    return {(float)c[0] / 255.0f, (float)c[1] / 255.0f, (float)c[2] / 255.0f, (float)c[3] / 255.0f};
+    const size_t i = (size_t)y * t.Width + x;
+    Vec4 r;
+    if (t.Format == IDKPT_TEX_RG32F) { const float* c = (const float*)t.Pixels + 2 * i; r = {c[0], c[1], 0.0f, 1.0f}; }
+    else if (t.Format == IDKPT_TEX_R32F) { r = {((const float*)t.Pixels)[i], 0.0f, 0.0f, 1.0f}; }
+    else if (t.Format == IDKPT_TEX_RGBA32F) { const float* c = (const float*)t.Pixels + 4 * i; r = {c[0], c[1], c[2], c[3]}; }
+    else {
+        const uint8_t* c = (const uint8_t*)t.Pixels + 4 * i;
+        if (t.Format == IDKPT_TEX_RGBA8_SRGB) { const float* lut = SrgbLut(); r = {lut[c[0]], lut[c[1]], lut[c[2]], (float)c[3] / 255.0f}; }
+        else r = {(float)c[0] / 255.0f, (float)c[1] / 255.0f, (float)c[2] / 255.0f, (float)c[3] / 255.0f};
+    }
+    if (t.Flags & IDKPT_TEX_FLAG_R_FROM_B) r.x = r.z;      // texture.SetSwizzleR(Swizzle.B), ModelLoader.cs:989-994
+    return r;
 }
 static inline Vec4 TexLerp(Vec4 a, Vec4 b, float t) {
     const float s = 1.0f - t;
@@ -946,17 +962,80 @@ static vec3 TurboColormap(float x) {
             d4(0.10667330f, 12.64194608f, -60.58204836f, 110.36276771f) + d2(-89.90310912f, 27.34824973f)};
 }
 
+// Persistent worker pool with dynamic chunking (round-1 verdict: spawning `threads` fresh std::threads per phase per bounce
+// made the CPU arm noisy by 2x between boxes). Workers are created once and parked on a condition variable; a job is a
+// range cut into chunks that the workers (and the calling thread, as worker 0) claim with an atomic counter, so uneven
+// rows / rays balance themselves. f(begin, end, workerId) may be called several times per worker.
+class WorkerPool {
+public:
+    static WorkerPool& get() { static WorkerPool p; return p; }
+    template <typename F>
+    void run(size_t n, int threads, F& f) {
+        std::unique_lock<std::mutex> runLock(runMutex_);          // one job at a time (callers are single-threaded anyway)
+        const int want = std::max(1, threads);
+        grow(want - 1);
+        const size_t chunk = std::max<size_t>(64, n / ((size_t)want * 8));
+        Job job;
+        job.n = n; job.chunk = chunk; job.next.store(0); job.active = want - 1;
+        job.fn = [&f](size_t b, size_t e, int tid) { f(b, e, tid); };
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = &job; generation_++; pending_ = want - 1;
+        }
+        cv_.notify_all();
+        work(job, 0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+        job_ = nullptr;
+    }
+private:
+    struct Job { size_t n, chunk; std::atomic<size_t> next; int active; std::function<void(size_t, size_t, int)> fn; };
+    static void work(Job& j, int tid) {
+        for (;;) {
+            const size_t b = j.next.fetch_add(j.chunk);
+            if (b >= j.n) break;
+            j.fn(b, std::min(j.n, b + j.chunk), tid);
+        }
+    }
+    void grow(int workers) {
+        while ((int)threads_.size() < workers) {
+            const int tid = (int)threads_.size() + 1;
+            threads_.emplace_back([this, tid]() {
+                uint64_t seen = 0;
+                for (;;) {
+                    Job* j = nullptr;
+                    {
+                        std::unique_lock<std::mutex> lk(m_);
+                        cv_.wait(lk, [&] { return stop_ || (generation_ != seen && job_ && tid <= job_->active); });
+                        if (stop_) return;
+                        seen = generation_;
+                        j = job_;
+                    }
+                    work(*j, tid);
+                    std::lock_guard<std::mutex> lk(m_);
+                    if (--pending_ == 0) done_.notify_all();
+                }
+            });
+        }
+    }
+    ~WorkerPool() {
+        { std::lock_guard<std::mutex> lk(m_); stop_ = true; }
+        cv_.notify_all();
+        for (auto& t : threads_) t.join();
+    }
+    std::mutex m_, runMutex_;
+    std::condition_variable cv_, done_;
+    std::vector<std::thread> threads_;
+    Job* job_ = nullptr;
+    uint64_t generation_ = 0;
+    int pending_ = 0;
+    bool stop_ = false;
+};
+
 template <typename F>
 static void parallel_for(size_t n, int threads, F f) {
     if (threads <= 1 || n < 256) { f(0, n, 0); return; }
-    std::vector<std::thread> pool;
-    size_t chunk = (n + threads - 1) / threads;
-    for (int t = 0; t < threads; t++) {
-        size_t b = std::min(n, (size_t)t * chunk), e = std::min(n, b + chunk);
-        if (b >= e) break;
-        pool.emplace_back([=]() { f(b, e, t); });
-    }
-    for (auto& th : pool) th.join();
+    WorkerPool::get().run(n, threads, f);
 }
 
 } // namespace

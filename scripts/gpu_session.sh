@@ -11,6 +11,8 @@ for s in $steps; do
     probe) timeout 900 python scripts/variant_probe.py --run --eighth > gpurun_out/variant_probe.log 2>&1; cut -c1-900 gpurun_out/variant_probe.log;;
     sweep) timeout 900 python scripts/variant_probe.py --run --eighth --sweep > gpurun_out/variant_probe.log 2>&1; cut -c1-900 gpurun_out/variant_probe.log;;
     bench) timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json;;
+    benchN) N=$(nvidia-smi -L | wc -l); timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; tail -5 gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.json;;
+    ref) timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json;;
     *) echo "unknown step $s";;
   esac
 done

@@ -160,3 +160,121 @@ def test_set_textures_replaces_the_table(textured):
     o = ol.path_trace(swapped, frame, s, w, h)
     assert np.array_equal(after.view(np.uint32), o.result.view(np.uint32))
     assert not np.array_equal(before, after)
+
+
+# ------------------------------------------------------------------------------------------------ block-compressed textures
+import os  # noqa: E402
+
+import bcn_ref  # noqa: E402
+
+
+def test_bcn_reference_decoders_match_pillow_golden_vectors():
+    """tests/bcn_ref.py (written from the BPTC / RGTC format definitions) against tests/golden/bcn_blocks.npz, decoded by an
+    independent implementation (Pillow's C decoder; generator: tests/golden/make_bcn_golden.py): every BC7 mode texel-exact;
+    BC5 / BC4 (decoded to float per the RGTC formulas) within half an 8-bit step of Pillow's integer results."""
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "bcn_blocks.npz"))
+    blocks, texels = g["bc7_blocks"], g["bc7_texels"]
+    seen = set()
+    for blk, want in zip(blocks, texels):
+        mode = 0
+        while mode < 8 and not (int(blk[0]) >> mode) & 1:
+            mode += 1
+        got = bcn_ref.decode_bc7_block(blk)
+        if mode == 8:
+            assert not got.any()          # reserved mode: (0,0,0,0) by the specification (Pillow writes opaque black)
+            continue
+        seen.add(mode)
+        assert np.array_equal(got, want), mode
+    assert seen == set(range(8))
+    for blk, want in zip(g["bc5_blocks"], g["bc5_texels"]):
+        r, gg = bcn_ref.decode_bc4_block(blk[:8]), bcn_ref.decode_bc4_block(blk[8:])
+        assert np.abs(r * 255.0 - want[..., 0]).max() < 0.87 and np.abs(gg * 255.0 - want[..., 1]).max() < 0.87
+    for blk, want in zip(g["bc4_blocks"], g["bc4_texels"]):
+        d = bcn_ref.decode_bc4_block(blk)
+        assert np.abs(d * 255.0 - want[..., 0]).max() < 0.87
+        pal_idx = [(int.from_bytes(bytes(blk[2:8]), "little") >> (3 * i)) & 7 for i in range(16)]
+        for i, k in enumerate(pal_idx):      # the two stored endpoints are exact
+            if k < 2:
+                assert d.reshape(16)[i] == np.float32(int(blk[k])) / np.float32(255.0)
+
+
+def compressed_variants(scene):
+    """(scene whose textures are BC7 / BC5 / BC4 block streams as the engine's KTX2 loader provides them,
+        the same scene with the textures decoded by tests/bcn_ref.py for the CPU oracle)."""
+    gpu, cpu = copy.copy(scene), copy.copy(scene)
+    gpu.textures, cpu.textures = [], []
+    rng = np.random.default_rng(77)
+    for k, t in enumerate(scene.textures):
+        px = t["pixels"]
+        h, w = px.shape[:2]
+        common = dict(wrap_s=t["wrap_s"], wrap_t=t["wrap_t"])
+        if k == 2:          # normal map -> BC5 (IDK_BC5_normal_metallicRoughness)
+            blocks = bcn_ref.encode_texture("bc5", px[..., :2])
+            gpu.textures.append(dict(format=capi.IDKPT_TEX_BC5_RG_UNORM, width=w, height=h, data=blocks, **common))
+            cpu.textures.append(dict(format=capi.IDKPT_TEX_RG32F, width=w, height=h, data=bcn_ref.decode_texture("bc5", blocks, w, h), **common))
+        elif k == 3:        # metallic-roughness -> BC7 unorm with the loader's R <- B swizzle; random blocks: every BC7 mode occurs
+            blocks = rng.integers(0, 256, (((h + 3) // 4) * ((w + 3) // 4), 16), dtype=np.uint8)
+            gpu.textures.append(dict(format=capi.IDKPT_TEX_BC7_UNORM, width=w, height=h, data=blocks, flags=capi.IDKPT_TEX_FLAG_R_FROM_B, **common))
+            cpu.textures.append(dict(pixels=bcn_ref.decode_texture("bc7", blocks, w, h), srgb=False, flags=capi.IDKPT_TEX_FLAG_R_FROM_B, **common))
+        elif k == 7:        # transmission -> BC4
+            blocks = bcn_ref.encode_texture("bc4", px[..., :1])
+            gpu.textures.append(dict(format=capi.IDKPT_TEX_BC4_R_UNORM, width=w, height=h, data=blocks, **common))
+            cpu.textures.append(dict(format=capi.IDKPT_TEX_R32F, width=w, height=h, data=bcn_ref.decode_texture("bc4", blocks, w, h), **common))
+        else:               # base colour / emissive -> BC7 sRGB
+            blocks = bcn_ref.encode_texture("bc7", px)
+            gpu.textures.append(dict(format=capi.IDKPT_TEX_BC7_SRGB if t["srgb"] else capi.IDKPT_TEX_BC7_UNORM, width=w, height=h, data=blocks, **common))
+            cpu.textures.append(dict(pixels=bcn_ref.decode_texture("bc7", blocks, w, h), srgb=t["srgb"], **common))
+    return gpu, cpu
+
+
+def test_oracle_accepts_float_textures_and_swizzle(textured):
+    scene, cam = textured
+    gpu, cpu = compressed_variants(scene)
+    w, h = 64, 48
+    frame = scenes.camera_frame(cam, w, h)
+    s = capi.default_settings()
+    a = ol.path_trace(scene, frame, s, w, h).result
+    b = ol.path_trace(cpu, frame, s, w, h).result
+    assert np.isfinite(b).all() and not np.array_equal(a, b)       # lossy compression + a noise metallic-roughness map change the image
+    assert np.abs(a[..., :3].mean() - b[..., :3].mean()) < 0.2      # ... but it is still the same room
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sorting", [0, 1])
+def test_gpu_block_compressed_textures_bit_exact(textured, sorting):
+    """BC7 (sRGB and unorm + R<-B swizzle, all 8 modes through a random-block image), BC5 and BC4 textures decoded by the CUDA
+    kernels at upload == the same textures decoded by the independent Python decoders and fed to the oracle uncompressed:
+    images, counters, AOVs, two accumulated samples."""
+    from idkengine_b200.pathtracer import PathTracer
+    scene, cam = textured
+    gpu, cpu = compressed_variants(scene)
+    w, h = 200, 120
+    frame = scenes.camera_frame(cam, w, h)
+    s = capi.default_settings()
+    s.RayDepth, s.DoRaySorting, s.OutputAOVs = 6, sorting, 1
+    with PathTracer(w, h, s) as pt:
+        pt.SetScene(gpu); pt.SetSky((0.6, 0.7, 0.9)); pt.SetFrame(frame)
+        pt.CollectStats = 1
+        st = [pt.Compute(), pt.Compute()]
+        img, alb, nrm = pt.Result, pt.AlbedoTexture, pt.NormalTexture
+    res = np.zeros((h, w, 4), np.float32)
+    ralb, rnrm = np.zeros_like(res), np.zeros_like(res)
+    o = ol.path_trace(cpu, frame, s, w, h, result=res, albedo=ralb, normal=rnrm)
+    o2 = ol.path_trace(cpu, frame, s, w, h, accumulated=o.accumulated, result=res, albedo=ralb, normal=rnrm)
+    assert st[0].Rays == o.stats.Rays and st[1].Rays == o2.stats.Rays and st[1].NodePairFetches == o2.stats.NodePairFetches
+    assert np.array_equal(img, res) and np.array_equal(alb, ralb) and np.array_equal(nrm, rnrm)
+
+
+@pytest.mark.gpu
+def test_gpu_rejects_malformed_texture_descs(textured):
+    from idkengine_b200.pathtracer import PathTracer, IdkPtError
+    scene, cam = textured
+    bad = copy.copy(scene)
+    bad.textures = [dict(t) for t in scene.textures]
+    bad.textures[0] = dict(format=42, width=8, height=8, data=np.zeros(256, np.uint8), wrap_s=10497, wrap_t=10497)
+    with PathTracer(32, 32) as pt:
+        with pytest.raises(IdkPtError):
+            pt.SetScene(bad)
+        bad.textures[0] = dict(format=capi.IDKPT_TEX_BC7_SRGB, width=8, height=8, data=np.zeros(64, np.uint8), wrap_s=10497, wrap_t=10497, flags=2)
+        with pytest.raises(IdkPtError):
+            pt.SetScene(bad)
