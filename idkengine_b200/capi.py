@@ -79,7 +79,7 @@ class IdkPtStats(ctypes.Structure):
         return d
 
 
-IDKPT_IMAGE_RESULT, IDKPT_IMAGE_ALBEDO, IDKPT_IMAGE_NORMAL, IDKPT_IMAGE_GATHERED = 0, 1, 2, 3
+IDKPT_IMAGE_RESULT, IDKPT_IMAGE_ALBEDO, IDKPT_IMAGE_NORMAL, IDKPT_IMAGE_GATHERED, IDKPT_IMAGE_DENOISED = 0, 1, 2, 3, 4
 IDKPT_GATHER_HANDLE_BYTES = 256
 IDKPT_ARRAY_MESH_TRANSFORMS, IDKPT_ARRAY_MESHES, IDKPT_ARRAY_MATERIALS, IDKPT_ARRAY_LIGHTS = 0, 1, 2, 3
 IDKPT_ARRAY_TLAS_NODES, IDKPT_ARRAY_BLAS_NODES, IDKPT_ARRAY_VERTEX_POSITIONS, IDKPT_ARRAY_VERTICES = 4, 5, 6, 7
@@ -94,7 +94,16 @@ EXPORTS = [
     "idkpt_result_device_ptr", "idkpt_tile_rows",
     "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_trace_rays_any", "idkpt_shadows_ray_traced",
     "idkpt_set_skinning_data", "idkpt_skin_vertices", "idkpt_blas_refit", "idkpt_read_range", "idkpt_post_process", "idkpt_ldr_device_ptr", "idkpt_abi_version",
+    "idkpt_denoise", "idkpt_denoise_device_ptrs", "idkpt_denoise_import_output",
 ]
+
+
+class IdkPtDenoiseSettings(ctypes.Structure):
+    _fields_ = [("Iterations", c_i32), ("SigmaColor", c_f), ("SigmaNormal", c_f), ("SigmaAlbedo", c_f), ("Demodulate", c_i32)]
+
+
+def default_denoise_settings():
+    return IdkPtDenoiseSettings(5, 3.0, 0.35, 0.25, 1)
 
 
 class IdkPtPostSettings(ctypes.Structure):
@@ -277,6 +286,12 @@ def load(path=None):
     L.idkpt_set_textures.argtypes = [c_vp, c_vp, c_u64]
     L.idkpt_sync.restype = c_i32
     L.idkpt_sync.argtypes = [c_vp]
+    L.idkpt_denoise.restype = c_i32
+    L.idkpt_denoise.argtypes = [c_vp, P(IdkPtDenoiseSettings), P(c_f)]
+    L.idkpt_denoise_device_ptrs.restype = c_i32
+    L.idkpt_denoise_device_ptrs.argtypes = [c_vp, P(c_vp), P(c_vp), P(c_vp), P(c_vp), P(c_u64)]
+    L.idkpt_denoise_import_output.restype = c_i32
+    L.idkpt_denoise_import_output.argtypes = [c_vp]
     L.idkpt_abi_version.restype = c_u32
     L.idkpt_abi_version.argtypes = []
     if path == _build.LIBIDKPT:

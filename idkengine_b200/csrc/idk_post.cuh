@@ -239,3 +239,81 @@ __global__ void __launch_bounds__(256) k_tonemap(TonemapArgs a) {
     const unsigned char b = (unsigned char)floorf(clamp1(c.z, 0.0f, 1.0f) * 255.0f + 0.5f);
     a.dst[(size_t)y * a.w + x] = make_uchar4(r, g, b, 255);
 }
+
+// ------------------------------------------------------------------------------------------------ denoise hand-off
+// PathTracerPipeline.Denoise (PathTracerPipeline.cs:165-194) downloads Result / Albedo / Normal as packed RGB floats into
+// OIDN buffers, runs the filter on the host side and uploads the output. Here the three images are packed into the same
+// OIDN layout (Format.Float3, width*height*3 floats) ON THE DEVICE -- an OIDN CUDA device can wrap those pointers with
+// oidnNewSharedBuffer, nothing crosses PCIe -- and, so that the chain also works without the OIDN library, a guided
+// edge-avoiding a-trous wavelet filter (Dammertz et al. 2010: 5x5 B3-spline taps, step 1, 2, 4, ..; colour / normal / albedo
+// edge-stopping weights, colour sigma halved per iteration; albedo demodulated before filtering and re-applied after) produces
+// the "Denoised" output texture. Deterministic fp32 (fixed tap order, no FMA, det_exp), restated by oracle/oracle_post.inc.
+struct DenoisePrepareArgs {
+    const float4* result; const float4* albedo; const float4* normal;
+    float* oidnBeauty; float* oidnAlbedo; float* oidnNormal;     // packed RGB floats (OIDN Format.Float3)
+    float4* work;                                                // filter input: (demodulated) colour
+    int count, demodulate;
+};
+
+__global__ void __launch_bounds__(256) k_denoise_prepare(DenoisePrepareArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.count) return;
+    const float4 c = a.result[i], al = a.albedo[i], n = a.normal[i];
+    a.oidnBeauty[3 * (size_t)i] = c.x; a.oidnBeauty[3 * (size_t)i + 1] = c.y; a.oidnBeauty[3 * (size_t)i + 2] = c.z;
+    a.oidnAlbedo[3 * (size_t)i] = al.x; a.oidnAlbedo[3 * (size_t)i + 1] = al.y; a.oidnAlbedo[3 * (size_t)i + 2] = al.z;
+    a.oidnNormal[3 * (size_t)i] = n.x; a.oidnNormal[3 * (size_t)i + 1] = n.y; a.oidnNormal[3 * (size_t)i + 2] = n.z;
+    f3 v = mk3(c.x, c.y, c.z);
+    if (a.demodulate) v = mk3(v.x / fmaxf(al.x, 0.001f), v.y / fmaxf(al.y, 0.001f), v.z / fmaxf(al.z, 0.001f));
+    a.work[i] = make_float4(v.x, v.y, v.z, 1.0f);
+}
+
+struct DenoiseAtrousArgs {
+    const float4* in; float4* out;
+    const float4* albedo; const float4* normal;
+    int w, h, step;
+    float invSigmaColor2, invSigmaNormal2, invSigmaAlbedo2, invStep2;
+};
+
+__global__ void __launch_bounds__(256) k_denoise_atrous(DenoiseAtrousArgs a) {
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= a.w || y >= a.h) return;
+    const size_t p = (size_t)y * a.w + x;
+    const float4 cp4 = a.in[p], ap4 = a.albedo[p], np4 = a.normal[p];
+    const f3 cp = mk3(cp4.x, cp4.y, cp4.z), ap = mk3(ap4.x, ap4.y, ap4.z), np_ = mk3(np4.x, np4.y, np4.z);
+    const float kw[3] = {0.375f, 0.25f, 0.0625f};
+    f3 sum = mk3(0.0f, 0.0f, 0.0f);
+    float wsum = 0.0f;
+    for (int dy = -2; dy <= 2; dy++) {
+        for (int dx = -2; dx <= 2; dx++) {
+            const int qx = x + dx * a.step, qy = y + dy * a.step;
+            if (qx < 0 || qy < 0 || qx >= a.w || qy >= a.h) continue;
+            const size_t q = (size_t)qy * a.w + qx;
+            const float4 cq4 = __ldg(a.in + q), aq4 = __ldg(a.albedo + q), nq4 = __ldg(a.normal + q);
+            const f3 cq = mk3(cq4.x, cq4.y, cq4.z);
+            const f3 dc = cq - cp, dn = mk3(nq4.x, nq4.y, nq4.z) - np_, da = mk3(aq4.x, aq4.y, aq4.z) - ap;
+            const float wc = fminf(det_exp(-(dot3(dc, dc) * a.invSigmaColor2)), 1.0f);
+            const float wn = fminf(det_exp(-(fmaxf(dot3(dn, dn) * a.invStep2, 0.0f) * a.invSigmaNormal2)), 1.0f);
+            const float wa = fminf(det_exp(-(dot3(da, da) * a.invSigmaAlbedo2)), 1.0f);
+            const float w = ((wc * wn) * wa) * (kw[dx < 0 ? -dx : dx] * kw[dy < 0 ? -dy : dy]);
+            sum = sum + cq * w;
+            wsum = wsum + w;
+        }
+    }
+    a.out[p] = make_float4(sum.x / wsum, sum.y / wsum, sum.z / wsum, 1.0f);
+}
+
+struct DenoiseFinishArgs {
+    const float4* filtered; const float4* albedo;
+    float4* denoised; float* oidnOutput;
+    int count, demodulate;
+};
+
+__global__ void __launch_bounds__(256) k_denoise_finish(DenoiseFinishArgs a) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.count) return;
+    const float4 c = a.filtered[i], al = a.albedo[i];
+    f3 v = mk3(c.x, c.y, c.z);
+    if (a.demodulate) v = mk3(v.x * fmaxf(al.x, 0.001f), v.y * fmaxf(al.y, 0.001f), v.z * fmaxf(al.z, 0.001f));
+    a.denoised[i] = make_float4(v.x, v.y, v.z, 1.0f);
+    a.oidnOutput[3 * (size_t)i] = v.x; a.oidnOutput[3 * (size_t)i + 1] = v.y; a.oidnOutput[3 * (size_t)i + 2] = v.z;
+}

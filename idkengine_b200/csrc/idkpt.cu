@@ -73,6 +73,9 @@ struct IdkPtCtx {
 
     // present chain: bloom mip chains (rgba16f), AgX constants, RGBA8 frame
     DevBuf bloomDown, bloomUp, postConsts, ldr;
+    // denoise hand-off: OIDN-layout packed RGB buffers (beauty, albedo, normal, output), a-trous ping-pong, denoised rgba32f image
+    DevBuf oidn[4], denoiseWork[2], denoised;
+    bool haveDenoised = false;
 
     // dynamic geometry: unskinned vertices, joint matrices, refit scratch (parents + locks of the largest BLAS)
     DevBuf unskinned, joints, refitParents, refitLocks;
@@ -545,7 +548,8 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
                      &ctx->meshes, &ctx->materials, &ctx->vertices, &ctx->lights, &ctx->tlas, &ctx->vtxFrame, &ctx->surfRec,
                      &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->counters, &ctx->countLog, &ctx->skyFaces,
                      &ctx->texPixels, &ctx->texRecs, &ctx->srgbLut, &ctx->bloomDown, &ctx->bloomUp, &ctx->postConsts, &ctx->ldr,
-                     &ctx->unskinned, &ctx->joints, &ctx->refitParents, &ctx->refitLocks, &ctx->scratch[0], &ctx->scratch[1], &ctx->scratch[2]};
+                     &ctx->unskinned, &ctx->joints, &ctx->refitParents, &ctx->refitLocks, &ctx->scratch[0], &ctx->scratch[1], &ctx->scratch[2],
+                     &ctx->oidn[0], &ctx->oidn[1], &ctx->oidn[2], &ctx->oidn[3], &ctx->denoiseWork[0], &ctx->denoiseWork[1], &ctx->denoised};
     for (DevBuf* b : all) release(*b);
     for (int i = 0; i < IDK_MAX_LANES; i++) release_lane(ctx->lanes[i], false);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
@@ -826,6 +830,9 @@ IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height) {
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->copyPending) { CK(cudaEventSynchronize(ctx->copyDone)); ctx->copyPending = false; }
     gather_teardown(ctx);   // the exported full-frame buffers have the old size: peers must export / import again
+    ctx->haveDenoised = false;
+    for (int i = 0; i < 4; i++) release(ctx->oidn[i]);
+    release(ctx->denoiseWork[0]); release(ctx->denoiseWork[1]); release(ctx->denoised);
     ctx->width = width;
     ctx->height = height;
     compute_tile_rows(ctx);
@@ -1172,6 +1179,14 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
 
 static int image_copy(IdkPtCtx* ctx, IdkPtImage which, void* host, uint64_t bytes, bool toHost) {
     if (!ctx || !host) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt image copy: null argument");
+    if (which == IDKPT_IMAGE_DENOISED) {
+        if (!toHost || !ctx->haveDenoised) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt image copy: no denoised image (call idkpt_denoise)");
+        if (bytes < (uint64_t)ctx->width * ctx->height * 16) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt image copy: buffer smaller than width*height*16");
+        CK(cudaSetDevice(ctx->device));
+        CK(cudaMemcpyAsync(host, ctx->denoised.p, (size_t)ctx->width * ctx->height * 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        return IDKPT_OK;
+    }
     if ((int)which < 0 || (int)which > 2) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt image copy: unknown image");
     if (bytes < (uint64_t)ctx->width * ctx->height * 16) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt image copy: buffer smaller than width*height*16");
     CK(cudaSetDevice(ctx->device));
@@ -1399,6 +1414,9 @@ IDKPT_API int idkpt_post_process(IdkPtCtx* ctx, const IdkPtPostSettings* s, IdkP
     if (source == IDKPT_IMAGE_GATHERED) {
         if (ctx->gatherWorld < 2 || ctx->gatherCurrent < 0) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: no gathered frame yet");
         src = (const float4*)ctx->gatherImage[ctx->gatherCurrent].p;
+    } else if (source == IDKPT_IMAGE_DENOISED) {
+        if (!ctx->haveDenoised) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: no denoised image (call idkpt_denoise)");
+        src = (const float4*)ctx->denoised.p;
     } else if ((int)source >= 0 && (int)source <= 2) {
         if (ctx->tileCount != 1) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_post_process: a tiled context holds only its own rows; use IDKPT_IMAGE_GATHERED");
         src = (const float4*)ctx->images[source].p;
@@ -1469,6 +1487,95 @@ IDKPT_API int idkpt_ldr_device_ptr(IdkPtCtx* ctx, void** devPtr, uint64_t* bytes
     if (!ctx->ldr.p) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_ldr_device_ptr: call idkpt_post_process first");
     *devPtr = ctx->ldr.p;
     if (bytes) *bytes = (uint64_t)ctx->width * ctx->height * 4;
+    return IDKPT_OK;
+}
+
+// ---- denoise hand-off ---------------------------------------------------------------------------------------
+static int denoise_alloc(IdkPtCtx* ctx) {
+    const size_t n = (size_t)ctx->width * ctx->height;
+    for (int i = 0; i < 4; i++) CK(ensure(ctx->oidn[i], n * 12));
+    for (int i = 0; i < 2; i++) CK(ensure(ctx->denoiseWork[i], n * 16));
+    CK(ensure(ctx->denoised, n * 16));
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_denoise(IdkPtCtx* ctx, const IdkPtDenoiseSettings* s, float* kernelMs) {
+    if (!ctx || !s) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_denoise: null argument");
+    if (kernelMs) *kernelMs = 0.0f;
+    if (ctx->tileCount != 1) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_denoise: the AOV images of a tiled context hold only its own rows");
+    if (s->Iterations < 0 || s->Iterations > 12 || !(s->SigmaColor > 0.0f) || !(s->SigmaNormal > 0.0f) || !(s->SigmaAlbedo > 0.0f))
+        return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_denoise: Iterations must be 0..12 and the sigmas positive");
+    DRAIN_PENDING("idkpt_denoise");
+    CK(cudaSetDevice(ctx->device));
+    int rc = denoise_alloc(ctx);
+    if (rc) return rc;
+    const int w = ctx->width, h = ctx->height, n = w * h;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->stream);
+    DenoisePrepareArgs pa;
+    pa.result = (const float4*)ctx->images[0].p; pa.albedo = (const float4*)ctx->images[1].p; pa.normal = (const float4*)ctx->images[2].p;
+    pa.oidnBeauty = (float*)ctx->oidn[0].p; pa.oidnAlbedo = (float*)ctx->oidn[1].p; pa.oidnNormal = (float*)ctx->oidn[2].p;
+    pa.work = (float4*)ctx->denoiseWork[0].p; pa.count = n; pa.demodulate = s->Demodulate ? 1 : 0;
+    k_denoise_prepare<<<(n + 255) / 256, 256, 0, ctx->stream>>>(pa);
+    int cur = 0;
+    for (int it = 0; it < s->Iterations; it++) {
+        const int step = 1 << it;
+        const float sc = s->SigmaColor / (float)step;
+        DenoiseAtrousArgs a;
+        a.in = (const float4*)ctx->denoiseWork[cur].p; a.out = (float4*)ctx->denoiseWork[cur ^ 1].p;
+        a.albedo = pa.albedo; a.normal = pa.normal; a.w = w; a.h = h; a.step = step;
+        a.invSigmaColor2 = 1.0f / (sc * sc); a.invSigmaNormal2 = 1.0f / (s->SigmaNormal * s->SigmaNormal);
+        a.invSigmaAlbedo2 = 1.0f / (s->SigmaAlbedo * s->SigmaAlbedo); a.invStep2 = 1.0f / ((float)step * (float)step);
+        k_denoise_atrous<<<dim3((unsigned)((w + 31) / 32), (unsigned)((h + 7) / 8)), 256, 0, ctx->stream>>>(a);
+        cur ^= 1;
+    }
+    if (s->Iterations > 0) {
+        DenoiseFinishArgs fa;
+        fa.filtered = (const float4*)ctx->denoiseWork[cur].p; fa.albedo = pa.albedo; fa.denoised = (float4*)ctx->denoised.p;
+        fa.oidnOutput = (float*)ctx->oidn[3].p; fa.count = n; fa.demodulate = pa.demodulate;
+        k_denoise_finish<<<(n + 255) / 256, 256, 0, ctx->stream>>>(fa);
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && kernelMs) cudaEventElapsedTime(kernelMs, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_denoise: ") + cudaGetErrorString(e); return IDKPT_ERR_CUDA; }
+    if (s->Iterations > 0) ctx->haveDenoised = true;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_denoise_device_ptrs(IdkPtCtx* ctx, void** beauty, void** albedo, void** normal, void** output, uint64_t* bytesEach) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    DRAIN_PENDING("idkpt_denoise_device_ptrs");
+    CK(cudaSetDevice(ctx->device));
+    int rc = denoise_alloc(ctx);
+    if (rc) return rc;
+    if (beauty) *beauty = ctx->oidn[0].p;
+    if (albedo) *albedo = ctx->oidn[1].p;
+    if (normal) *normal = ctx->oidn[2].p;
+    if (output) *output = ctx->oidn[3].p;
+    if (bytesEach) *bytesEach = (uint64_t)ctx->width * ctx->height * 12;
+    return IDKPT_OK;
+}
+
+// The OIDN output buffer (written by the host's OIDN CUDA device) becomes the denoised image.
+__global__ void __launch_bounds__(256) k_denoise_import(const float* __restrict__ rgb, float4* __restrict__ out, int count) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < count) out[i] = make_float4(rgb[3 * (size_t)i], rgb[3 * (size_t)i + 1], rgb[3 * (size_t)i + 2], 1.0f);
+}
+
+IDKPT_API int idkpt_denoise_import_output(IdkPtCtx* ctx) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    DRAIN_PENDING("idkpt_denoise_import_output");
+    if (!ctx->oidn[3].p || !ctx->denoised.p) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_denoise_import_output: call idkpt_denoise_device_ptrs / idkpt_denoise first");
+    CK(cudaSetDevice(ctx->device));
+    const int n = ctx->width * ctx->height;
+    k_denoise_import<<<(n + 255) / 256, 256, 0, ctx->stream>>>((const float*)ctx->oidn[3].p, (float4*)ctx->denoised.p, n);
+    CK(cudaGetLastError());
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->haveDenoised = true;
     return IDKPT_OK;
 }
 

@@ -86,6 +86,29 @@ class PathTracer:
                     "idkpt_post_process")
         return out, ms.value
 
+    # ------------------------------------------------------------------ denoise hand-off (PathTracerPipeline.Denoise, PathTracerPipeline.cs:165-194)
+    def Denoise(self, settings=None):
+        """Pack Result / Albedo / Normal into the OIDN-layout device buffers and run the built-in guided a-trous filter.
+        Returns kernel ms; the output is `Denoised` (and PostProcess(source=IDKPT_IMAGE_DENOISED))."""
+        st = settings if settings is not None else capi.default_denoise_settings()
+        ms = ctypes.c_float()
+        self._check(self._lib.idkpt_denoise(self._ctx, ctypes.byref(st), ctypes.byref(ms)), "idkpt_denoise")
+        return ms.value
+
+    @property
+    def Denoised(self):
+        return self._read(capi.IDKPT_IMAGE_DENOISED)
+
+    def DenoiseDevicePtrs(self):
+        """(beauty, albedo, normal, output) device pointers of the packed-RGB float buffers (OIDN Format.Float3) and their size."""
+        p = [ctypes.c_void_p() for _ in range(4)]
+        n = ctypes.c_uint64()
+        self._check(self._lib.idkpt_denoise_device_ptrs(self._ctx, *[ctypes.byref(x) for x in p], ctypes.byref(n)), "idkpt_denoise_device_ptrs")
+        return [x.value for x in p], n.value
+
+    def DenoiseImportOutput(self):
+        self._check(self._lib.idkpt_denoise_import_output(self._ctx), "idkpt_denoise_import_output")
+
     # ------------------------------------------------------------------ dynamic geometry (ModelManager.Update, ModelManager.cs:236-261)
     def SetSkinningData(self, unskinned):
         unskinned = np.ascontiguousarray(unskinned)

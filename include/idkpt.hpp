@@ -129,6 +129,8 @@ public:
     // ---- presentation / interop -------------------------------------------------------------------------------------------
     void PresentAsync(void* pinnedHostRgba32f, uint64_t bytes, IdkPtImage which = IDKPT_IMAGE_RESULT) { check(idkpt_present_async(ctx_, which, pinnedHostRgba32f, bytes), "idkpt_present_async"); }
     void PresentWait() { check(idkpt_present_wait(ctx_), "idkpt_present_wait"); }
+    float Denoise(const IdkPtDenoiseSettings& s) { float ms = 0.0f; check(idkpt_denoise(ctx_, &s, &ms), "idkpt_denoise"); return ms; }   // PathTracerPipeline.Denoise
+    std::vector<float> Denoised() const { return read(IDKPT_IMAGE_DENOISED); }
     void RegisterHostBuffer(void* hostPtr, uint64_t bytes) { check(idkpt_register_host_buffer(ctx_, hostPtr, bytes), "idkpt_register_host_buffer"); }
     void UnregisterHostBuffer(void* hostPtr) { check(idkpt_unregister_host_buffer(ctx_, hostPtr), "idkpt_unregister_host_buffer"); }
     // Bloom + TonemapAndGammaCorrect -> RGBA8 (Application.cs:217-223); out may be null to keep the frame on the device

@@ -281,3 +281,18 @@ def synth_gbuffer(scene, frame, width, height):
     mat = scene.materials[mesh["MaterialId"]]
     mr = np.stack([np.clip(mat["MetallicFactor"] + mesh["SpecularBias"], 0, 1), np.clip(mat["RoughnessFactor"] + mesh["RoughnessBias"], 0, 1)], 1).astype(np.float32)
     return depth.reshape(height, width), nrg.reshape(height, width, 2), mr.reshape(height, width, 2)
+
+
+def denoise(result, albedo, normal, settings=None, threads=None):
+    """oracle_denoise: the guided a-trous filter of csrc/idk_post.cuh on rgba32f images [H, W, 4] -> denoised [H, W, 4]."""
+    st = settings if settings is not None else capi.default_denoise_settings()
+    h, w = result.shape[:2]
+    r, a, n = (np.ascontiguousarray(x, np.float32) for x in (result, albedo, normal))
+    out = np.zeros((h, w, 4), np.float32)
+    L = lib()
+    L.oracle_denoise.restype = ctypes.c_int32
+    L.oracle_denoise.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.POINTER(capi.IdkPtDenoiseSettings),
+                                 ctypes.c_void_p, ctypes.c_int32]
+    rc = L.oracle_denoise(r.ctypes.data, a.ctypes.data, n.ctypes.data, w, h, ctypes.byref(st), out.ctypes.data, threads or default_threads())
+    assert rc == 0
+    return out

@@ -94,3 +94,75 @@ def test_post_process_errors():
     with PathTracer(1, 1) as pt:
         with pytest.raises(RuntimeError):
             pt.PostProcess()                                 # bloom needs 2x2
+
+
+# ------------------------------------------------------------------------------------------------ denoise hand-off (8f.3)
+def noisy_scene_images(w=96, h=64, seed=3):
+    """A piecewise-flat 'render' with heavy noise plus clean albedo / normal guides: two materials split by an edge."""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    left = (xx < w // 2)[..., None]
+    albedo = np.where(left, np.array([0.8, 0.2, 0.2], np.float32), np.array([0.2, 0.3, 0.9], np.float32)).astype(np.float32)
+    normal = np.where(left, np.array([0.0, 0.0, 1.0], np.float32), np.array([1.0, 0.0, 0.0], np.float32)).astype(np.float32)
+    light = (0.5 + 0.5 * yy / h)[..., None].astype(np.float32)
+    clean = albedo * light
+    noisy = clean * rng.uniform(0.2, 1.8, (h, w, 1)).astype(np.float32)
+    pad = lambda a: np.concatenate([a, np.ones((h, w, 1), np.float32)], -1)
+    return pad(noisy.astype(np.float32)), pad(albedo), pad(normal), clean
+
+
+def test_oracle_denoise_reduces_noise_and_keeps_edges():
+    noisy, albedo, normal, clean = noisy_scene_images()
+    out = ol.denoise(noisy, albedo, normal)
+    err_in = np.abs(noisy[..., :3] - clean).mean()
+    err_out = np.abs(out[..., :3] - clean).mean()
+    assert err_out < 0.35 * err_in                       # the noise is mostly gone
+    w = noisy.shape[1]
+    # ... and nothing bled across the material edge: both sides keep their own hue
+    assert out[:, w // 2 - 3, 0].mean() > 2.0 * out[:, w // 2 - 3, 2].mean()
+    assert out[:, w // 2 + 3, 2].mean() > 2.0 * out[:, w // 2 + 3, 0].mean()
+    assert np.all(out[..., 3] == 1.0)
+    st = capi.default_denoise_settings()
+    st.Iterations = 0
+    assert np.array_equal(ol.denoise(noisy, albedo, normal, st)[..., :3], noisy[..., :3] / np.maximum(albedo[..., :3], np.float32(0.001)) * np.maximum(albedo[..., :3], np.float32(0.001)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("demod", [1, 0])
+def test_gpu_denoise_bit_exact_and_oidn_buffers(demod):
+    """idkpt_denoise on a real low-sample render with AOVs == oracle_denoise, bit for bit; the OIDN-layout device buffers
+    hold the packed RGB floats Texture.Download(PixelFormat.RGB, Float) would produce; the denoised image feeds the present chain."""
+    import torch
+    from idkengine_b200 import multigpu
+    from idkengine_b200.pathtracer import PathTracer
+    scene, cam = scenes.cornell_1k(threads=1)
+    w, h = 160, 104
+    s = capi.default_settings()
+    s.OutputAOVs = 1
+    st = capi.default_denoise_settings()
+    st.Demodulate = demod
+    with PathTracer(w, h, s) as pt:
+        pt.SetScene(scene); pt.SetSky((0.6, 0.7, 0.9)); pt.SetFrame(scenes.camera_frame(cam, w, h))
+        for _ in range(4):
+            pt.Compute()
+        res, alb, nrm = pt.Result, pt.AlbedoTexture, pt.NormalTexture
+        ms = pt.Denoise(st)
+        den = pt.Denoised
+        ptrs, nbytes = pt.DenoiseDevicePtrs()
+        assert nbytes == w * h * 12
+        packed = [torch.as_tensor(multigpu.DeviceArray(p, (h, w, 3)), device="cuda").cpu().numpy() for p in ptrs]
+        ldr, _ = pt.PostProcess(source=capi.IDKPT_IMAGE_DENOISED)
+        # the OIDN path: an external filter writes the output buffer, the library adopts it
+        out_t = torch.as_tensor(multigpu.DeviceArray(ptrs[3], (h, w, 3)), device="cuda")
+        out_t.copy_(torch.as_tensor(multigpu.DeviceArray(ptrs[0], (h, w, 3)), device="cuda") * 0.5)
+        torch.cuda.synchronize()
+        pt.DenoiseImportOutput()
+        adopted = pt.Denoised
+    want = ol.denoise(res, alb, nrm, st)
+    assert ms > 0 and np.array_equal(den.view(np.uint32), want.view(np.uint32))
+    assert np.array_equal(packed[0], res[..., :3]) and np.array_equal(packed[1], alb[..., :3]) and np.array_equal(packed[2], nrm[..., :3])
+    assert np.array_equal(packed[3], den[..., :3])
+    assert np.array_equal(ldr, ol.post_process(want))
+    assert np.array_equal(adopted[..., :3], res[..., :3] * np.float32(0.5)) and np.all(adopted[..., 3] == 1.0)
+    noise_in = np.abs(np.diff(res[..., :3], axis=1)).mean()
+    assert np.abs(np.diff(den[..., :3], axis=1)).mean() < 0.6 * noise_in
