@@ -965,7 +965,43 @@ __device__ __forceinline__ void surface_textured(const DeviceScene& sc, int mesh
     s.TintOnTransmissive = mesh.TintOnTransmissive != 0;
 }
 
-// texture(skyBoxUBO.Albedo, dir).rgb: GL cube-map face selection (spec table 8.19), bilinear inside the face, clamp to edge.
+// GL_TEXTURE_CUBE_MAP_SEAMLESS (the engine enables it: SkyBoxManager.cs:74): a bilinear footprint that leaves the face takes
+// the texel from the face across that edge (OpenGL 4.6 spec 8.17, "seamless cube map filtering"); at a cube corner, where no
+// face holds the fourth texel, the three defined texels are averaged. Coordinates are kept as odd integers c = 2*texel+1-size
+// (texel centres in units of 1/size on the cube [-size, size]^3), so folding over an edge is exact integer arithmetic.
+__device__ __forceinline__ void sky_face_to_cube(int face, int sc, int tc, int size, int& X, int& Y, int& Z) {
+    switch (face) {   // spec table 8.19 inverted: +X (ma, -tc, -sc), -X (-ma, -tc, sc), +Y (sc, ma, tc), -Y (sc, -ma, -tc), +Z (sc, -tc, ma), -Z (-sc, -tc, -ma)
+        case 0: X = size; Y = -tc; Z = -sc; break;
+        case 1: X = -size; Y = -tc; Z = sc; break;
+        case 2: X = sc; Y = size; Z = tc; break;
+        case 3: X = sc; Y = -size; Z = -tc; break;
+        case 4: X = sc; Y = -tc; Z = size; break;
+        default: X = -sc; Y = -tc; Z = -size; break;
+    }
+}
+__device__ __forceinline__ f3 sky_texel_in(const DeviceScene& sc, int face, int x, int y) {
+    const float4 t = __ldg(sc.skyFaces + ((size_t)face * sc.skyFaceSize + y) * sc.skyFaceSize + x);
+    return mk3(t.x, t.y, t.z);
+}
+// texel (x, y) of `face` where x or y (not both) may lie one texel outside the face
+__device__ __forceinline__ f3 sky_texel_edge(const DeviceScene& sc, int face, int x, int y) {
+    const int size = sc.skyFaceSize;
+    if (x >= 0 && x < size && y >= 0 && y < size) return sky_texel_in(sc, face, x, y);
+    int s2 = 2 * x + 1 - size, t2 = 2 * y + 1 - size;     // |.| == size + 1 for the coordinate that left the face
+    int X, Y, Z;
+    sky_face_to_cube(face, s2, t2, size, X, Y, Z);
+    // fold the overhang (1 unit) over the edge: the in-plane coordinate stops at the cube surface, the old major axis retreats by it
+    if (X > size || X < -size) { X = X > 0 ? size : -size; if (Y == size || Y == -size) Y += Y > 0 ? -1 : 1; else Z += Z > 0 ? -1 : 1; }
+    else if (Y > size || Y < -size) { Y = Y > 0 ? size : -size; if (X == size || X == -size) X += X > 0 ? -1 : 1; else Z += Z > 0 ? -1 : 1; }
+    else { Z = Z > 0 ? size : -size; if (X == size || X == -size) X += X > 0 ? -1 : 1; else Y += Y > 0 ? -1 : 1; }
+    int nf, ns, nt;
+    if (X == size) { nf = 0; ns = -Z; nt = -Y; } else if (X == -size) { nf = 1; ns = Z; nt = -Y; }
+    else if (Y == size) { nf = 2; ns = X; nt = Z; } else if (Y == -size) { nf = 3; ns = X; nt = -Z; }
+    else if (Z == size) { nf = 4; ns = X; nt = -Y; } else { nf = 5; ns = -X; nt = -Y; }
+    return sky_texel_in(sc, nf, (ns + size - 1) / 2, (nt + size - 1) / 2);
+}
+
+// texture(skyBoxUBO.Albedo, dir).rgb: GL cube-map face selection (spec table 8.19), bilinear filtering, seamless across edges.
 __device__ __forceinline__ f3 sample_sky(const DeviceScene& sc, f3 d) {
     if (sc.skyFaceSize == 0) return mk3(sc.skyR, sc.skyG, sc.skyB);
     const int size = sc.skyFaceSize;
@@ -979,13 +1015,24 @@ __device__ __forceinline__ f3 sample_sky(const DeviceScene& sc, f3 d) {
     const float px = s * (float)size - 0.5f, py = t * (float)size - 0.5f;
     const float fx0 = floorf(px), fy0 = floorf(py);
     const float fx = px - fx0, fy = py - fy0;
-    const int x0 = min(max((int)fx0, 0), size - 1), x1 = min(max((int)fx0 + 1, 0), size - 1);
-    const int y0 = min(max((int)fy0, 0), size - 1), y1 = min(max((int)fy0 + 1, 0), size - 1);
-    const float4* fp = sc.skyFaces + (size_t)face * size * size;
-    const float4 t00 = __ldg(fp + (size_t)y0 * size + x0), t10 = __ldg(fp + (size_t)y0 * size + x1);
-    const float4 t01 = __ldg(fp + (size_t)y1 * size + x0), t11 = __ldg(fp + (size_t)y1 * size + x1);
-    const f3 a = mix3(mk3(t00.x, t00.y, t00.z), mk3(t10.x, t10.y, t10.z), fx);
-    const f3 b = mix3(mk3(t01.x, t01.y, t01.z), mk3(t11.x, t11.y, t11.z), fx);
+    const int x0 = (int)fx0, x1 = (int)fx0 + 1, y0 = (int)fy0, y1 = (int)fy0 + 1;      // each in [-1, size]
+    const bool ox0 = x0 < 0, ox1 = x1 >= size, oy0 = y0 < 0, oy1 = y1 >= size;
+    f3 t00, t10, t01, t11;
+    if ((ox0 || ox1) && (oy0 || oy1)) {
+        // cube corner: exactly one of the four texels lies outside in both directions; it is the mean of the other three
+        const bool c00 = ox0 && oy0, c10 = ox1 && oy0, c01 = ox0 && oy1;
+        t00 = c00 ? mk3(0, 0, 0) : sky_texel_edge(sc, face, x0, y0);
+        t10 = c10 ? mk3(0, 0, 0) : sky_texel_edge(sc, face, x1, y0);
+        t01 = c01 ? mk3(0, 0, 0) : sky_texel_edge(sc, face, x0, y1);
+        t11 = (c00 || c10 || c01) ? sky_texel_edge(sc, face, x1, y1) : mk3(0, 0, 0);
+        const f3 mean = ((t00 + t10) + (t01 + t11)) / 3.0f;
+        if (c00) t00 = mean; else if (c10) t10 = mean; else if (c01) t01 = mean; else t11 = mean;
+    } else {
+        t00 = sky_texel_edge(sc, face, x0, y0); t10 = sky_texel_edge(sc, face, x1, y0);
+        t01 = sky_texel_edge(sc, face, x0, y1); t11 = sky_texel_edge(sc, face, x1, y1);
+    }
+    const f3 a = mix3(t00, t10, fx);
+    const f3 b = mix3(t01, t11, fx);
     return mix3(a, b, fy);
 }
 

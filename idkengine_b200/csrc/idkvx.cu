@@ -245,8 +245,10 @@ IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats) {
         // levels that halve exactly on every axis and are big enough to fill the machine take the shared-memory tiled kernel
         const VxGridDev& gd = ctx->grid;
         const bool halves = gd.sx[l - 1] == 2 * gd.sx[l] && gd.sy[l - 1] == 2 * gd.sy[l] && gd.sz[l - 1] == 2 * gd.sz[l];
-        const bool tiledOff = getenv("IDKVX_MIP_TILED") && atoi(getenv("IDKVX_MIP_TILED")) == 0;      // developer knob (cross-check)
-        if (halves && n >= 4096 && !tiledOff) {
+        // measured on B200 (bench.py vxgi record, 384^3): tiled 0.82 ms vs 0.43 ms for the direct kernel -- the direct kernel's 7x
+        // re-reads are L1 hits and the filter is bound by its ~640 fp32 operations per texel, not by memory; opt-in only (cross-check)
+        const bool tiledOn = getenv("IDKVX_MIP_TILED") && atoi(getenv("IDKVX_MIP_TILED")) != 0;
+        if (halves && n >= 4096 && tiledOn) {
             const int tiles = ((gd.sx[l] + IDKVX_MT_X - 1) / IDKVX_MT_X) * ((gd.sy[l] + IDKVX_MT_Y - 1) / IDKVX_MT_Y) * ((gd.sz[l] + IDKVX_MT_Z - 1) / IDKVX_MT_Z);
             k_vx_mipmap_tiled<<<std::min(tiles, ctx->smCount * 4), 256, IDKVX_MIP_TILE_SMEM, ctx->stream>>>(ctx->grid, l);
         } else {

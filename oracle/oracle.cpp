@@ -551,10 +551,47 @@ static inline vec3 SampleSky(const float* const faces[6], int size, const float*
     const float px = s * (float)size - 0.5f, py = t * (float)size - 0.5f;
     const float fx0 = floorf(px), fy0 = floorf(py);
     const float fx = px - fx0, fy = py - fy0;
-    auto cl = [&](int v) { return v < 0 ? 0 : (v > size - 1 ? size - 1 : v); };
-    const int x0 = cl((int)fx0), x1 = cl((int)fx0 + 1), y0 = cl((int)fy0), y1 = cl((int)fy0 + 1);
-    auto tx = [&](int x, int y) { const float* p = faces[face] + 4 * ((size_t)y * size + x); return V(p[0], p[1], p[2]); };
-    const vec3 a = mix(tx(x0, y0), tx(x1, y0), fx), b = mix(tx(x0, y1), tx(x1, y1), fx);
+    // GL_TEXTURE_CUBE_MAP_SEAMLESS (SkyBoxManager.cs:74; OpenGL 4.6 spec 8.17): texels beyond an edge come from the face across
+    // it; the missing fourth texel at a cube corner is the mean of the other three. Texel centres as odd integers
+    // c = 2*texel + 1 - size on the cube [-size, size]^3: crossing an edge is an exact integer fold.
+    const int x0 = (int)fx0, x1 = x0 + 1, y0 = (int)fy0, y1 = y0 + 1;
+    auto inside = [&](int f, int x, int y) { const float* p = faces[f] + 4 * ((size_t)y * size + x); return V(p[0], p[1], p[2]); };
+    auto tx = [&](int x, int y) -> vec3 {
+        if (x >= 0 && x < size && y >= 0 && y < size) return inside(face, x, y);
+        const int s2 = 2 * x + 1 - size, t2 = 2 * y + 1 - size;
+        int P[3];
+        switch (face) {
+            case 0: P[0] = size; P[1] = -t2; P[2] = -s2; break;
+            case 1: P[0] = -size; P[1] = -t2; P[2] = s2; break;
+            case 2: P[0] = s2; P[1] = size; P[2] = t2; break;
+            case 3: P[0] = s2; P[1] = -size; P[2] = -t2; break;
+            case 4: P[0] = s2; P[1] = -t2; P[2] = size; break;
+            default: P[0] = -s2; P[1] = -t2; P[2] = -size; break;
+        }
+        const int major = face >> 1;                       // axis of the face we came from
+        int over = -1;
+        for (int k = 0; k < 3; k++) if (P[k] > size || P[k] < -size) over = k;
+        P[over] = P[over] > 0 ? size : -size;              // the overhanging coordinate lands on the neighbouring face ...
+        P[major] += P[major] > 0 ? -1 : 1;                 // ... one half-texel step in from the shared edge
+        int nf, ns, nt;
+        if (over == 0) { nf = P[0] > 0 ? 0 : 1; ns = P[0] > 0 ? -P[2] : P[2]; nt = -P[1]; }
+        else if (over == 1) { nf = P[1] > 0 ? 2 : 3; ns = P[0]; nt = P[1] > 0 ? P[2] : -P[2]; }
+        else { nf = P[2] > 0 ? 4 : 5; ns = P[2] > 0 ? P[0] : -P[0]; nt = -P[1]; }
+        return inside(nf, (ns + size - 1) / 2, (nt + size - 1) / 2);
+    };
+    const bool ox0 = x0 < 0, ox1 = x1 >= size, oy0 = y0 < 0, oy1 = y1 >= size;
+    vec3 t00, t10, t01, t11;
+    if ((ox0 || ox1) && (oy0 || oy1)) {
+        const bool c00 = ox0 && oy0, c10 = ox1 && oy0, c01 = ox0 && oy1;
+        const vec3 zero = V(0, 0, 0);
+        t00 = c00 ? zero : tx(x0, y0); t10 = c10 ? zero : tx(x1, y0); t01 = c01 ? zero : tx(x0, y1);
+        t11 = (c00 || c10 || c01) ? tx(x1, y1) : zero;
+        const vec3 mean = ((t00 + t10) + (t01 + t11)) / 3.0f;
+        if (c00) t00 = mean; else if (c10) t10 = mean; else if (c01) t01 = mean; else t11 = mean;
+    } else {
+        t00 = tx(x0, y0); t10 = tx(x1, y0); t01 = tx(x0, y1); t11 = tx(x1, y1);
+    }
+    const vec3 a = mix(t00, t10, fx), b = mix(t01, t11, fx);
     return mix(a, b, fy);
 }
 
@@ -1253,6 +1290,16 @@ ORACLE_API int oracle_path_trace(const IdkPtSceneDesc* scene, const IdkPtSkyDesc
         }
     }
     return 0;
+}
+
+// texture(samplerCube, dir) on its own (unit tests of the seamless filtering)
+ORACLE_API void oracle_sample_sky(const IdkPtSkyDesc* sky, const float* dirs, uint64_t n, float* out3) {
+    const float* faces[6];
+    for (int i = 0; i < 6; i++) faces[i] = sky->Faces[i];
+    for (uint64_t i = 0; i < n; i++) {
+        const vec3 c = SampleSky(faces, sky->FaceSize, sky->Color, V(dirs + 3 * i));
+        out3[3 * i] = c.x; out3[3 * i + 1] = c.y; out3[3 * i + 2] = c.z;
+    }
 }
 
 // exposed for unit tests of the deterministic math against libm

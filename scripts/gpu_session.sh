@@ -13,6 +13,13 @@ for s in $steps; do
     bench) timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json;;
     benchN) N=$(nvidia-smi -L | wc -l); timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; tail -5 gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.json;;
     ref) timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json;;
+    ncu) # launch list of the bench command (shares of the step) + --set full captures of the dominant kernels (never a bench number)
+       timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity --no-vxgi > gpurun_out/bench_under_ncu.log 2>&1
+       timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_traverse2 -s 8 -c 3 -f -o gpurun_out/prof_traverse2_r02 python scripts/ncu_target.py pt > gpurun_out/ncu_t2.log 2>&1
+       timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_shade -s 9 -c 2 -f -o gpurun_out/prof_shade_r02 python scripts/ncu_target.py pt > gpurun_out/ncu_shade.log 2>&1
+       timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_compact -s 8 -c 2 -f -o gpurun_out/prof_compact_r02 python scripts/ncu_target.py pt > gpurun_out/ncu_compact.log 2>&1
+       timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_vx_ -c 14 -f -o gpurun_out/prof_vxgi_r02 python scripts/ncu_target.py vxgi > gpurun_out/ncu_vx.log 2>&1
+       ls -la gpurun_out/*.ncu-rep; tail -2 gpurun_out/ncu_t2.log;;
     *) echo "unknown step $s";;
   esac
 done

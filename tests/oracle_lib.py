@@ -296,3 +296,15 @@ def denoise(result, albedo, normal, settings=None, threads=None):
     rc = L.oracle_denoise(r.ctypes.data, a.ctypes.data, n.ctypes.data, w, h, ctypes.byref(st), out.ctypes.data, threads or default_threads())
     assert rc == 0
     return out
+
+
+def sample_sky(faces, dirs):
+    """texture(samplerCube, dir).rgb for float32 faces [6, N, N, 4] and directions [M, 3]."""
+    sk = capi.sky_desc((0.0, 0.0, 0.0), faces)
+    d = np.ascontiguousarray(dirs, np.float32)
+    out = np.zeros((len(d), 3), np.float32)
+    L = lib()
+    L.oracle_sample_sky.restype = None
+    L.oracle_sample_sky.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p]
+    L.oracle_sample_sky(ctypes.byref(sk), d.ctypes.data, len(d), out.ctypes.data)
+    return out

@@ -77,3 +77,48 @@ def test_any_hit_is_monotone_in_tmax(multi_blas):
         assert (occ | ~prev).all()                                      # once occluded, stays occluded for a longer ray
         prev = occ
     assert prev.mean() > 0.3
+
+
+def _cube_face_dirs(size):
+    """Direction through every texel centre of the six faces, GL layout (+X,-X,+Y,-Y,+Z,-Z; spec table 8.19)."""
+    c = (np.arange(size, dtype=np.float64) + 0.5) / size * 2.0 - 1.0
+    sc, tc = np.meshgrid(c, c)                      # [t, s]
+    one = np.ones_like(sc)
+    return np.stack([np.stack([one, -tc, -sc], -1), np.stack([-one, -tc, sc], -1), np.stack([sc, one, tc], -1),
+                     np.stack([sc, -one, -tc], -1), np.stack([sc, -tc, one], -1), np.stack([-sc, -tc, -one], -1)])
+
+
+def test_cube_map_filtering_is_seamless():
+    """GL_TEXTURE_CUBE_MAP_SEAMLESS (the engine enables it, SkyBoxManager.cs:74): a cube map that stores a smooth function of
+    the direction must be reproduced smoothly ACROSS face edges and corners, not only inside faces. With per-face clamping the
+    error at an edge is half a texel of gradient; with seamless filtering it stays at the curvature level everywhere."""
+    import oracle_lib as ol
+    size = 16
+    dirs = _cube_face_dirs(size)
+    unit = dirs / np.linalg.norm(dirs, axis=-1, keepdims=True)
+    faces = np.zeros((6, size, size, 4), np.float32)
+    faces[..., :3] = (0.5 + 0.5 * unit).astype(np.float32)          # f(d) = 0.5 + 0.5 d
+    faces[..., 3] = 1.0
+    # texel centres return the texel exactly
+    flat = dirs.reshape(-1, 3)
+    got = ol.sample_sky(faces, flat)
+    assert np.abs(got - faces[..., :3].reshape(-1, 3)).max() < 1e-6
+    # random directions, with a bias towards edges and corners of the cube
+    rng = np.random.default_rng(12)
+    d = rng.normal(size=(60000, 3))
+    d[:20000] = np.sign(d[:20000]) * (1.0 - rng.uniform(0, 0.08, (20000, 3)) * rng.integers(0, 2, (20000, 3)))   # near edges / corners
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    got = ol.sample_sky(faces, d)
+    want = 0.5 + 0.5 * d
+    err = np.abs(got - want).max(axis=1)
+    # bilinear interpolation of a smooth function on this grid: a few 1e-3; a clamped edge would be ~0.5 * (2/size) * 0.5 = 0.03
+    assert err.max() < 0.012, err.max()
+    m = np.abs(d).max(axis=1, keepdims=True)
+    on_cube = d / m
+    near_edge = (np.sort(np.abs(on_cube), axis=1)[:, 1] > 1.0 - 1.0 / size)
+    assert near_edge.sum() > 5000 and err[near_edge].max() < 0.012
+    # continuity: two directions a hair apart on either side of an edge give (almost) the same colour
+    a = np.array([[1.0, 0.3, 0.999999], [1.0, 0.3, 1.000001]])
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    s2 = ol.sample_sky(faces, a)
+    assert np.abs(s2[0] - s2[1]).max() < 1e-4
