@@ -9,6 +9,7 @@
 #pragma once
 #include <cuda_fp16.h>
 #include "idk_device.cuh"
+#include "idk_shadows.cuh"
 #include "../../include/idk_gpu_types.h"
 
 #define IDKVX_MAX_LEVELS 16
@@ -35,6 +36,8 @@ struct VxScene {
     uint32_t lightCount;
     const TexRec* textures;        // material texture table (idkpt.h IdkPtTextureDesc), handle k = textures[k - 1]
     const float* srgbLut;
+    DeviceScene occ;               // the path tracer's device scene: occluders of the point-shadowed lights (idkvx_set_shadow_tracer)
+    int occValid;
 };
 
 __device__ __forceinline__ float det_tan(float x) { float s, c; det_sincos(x, &s, &c); return s / c; }
@@ -94,7 +97,7 @@ __device__ __forceinline__ void vx_setup(const VxScene& sc, const VxGridDev& g, 
 }
 
 // one pixel centre (i, j) of the projection plane; returns true if a voxel was written
-__device__ __forceinline__ bool vx_pixel(const VxScene& sc, const VxGridDev& g, const VxTri& t, int i, int j) {
+__device__ __forceinline__ bool vx_pixel(const VxScene& sc, const VxGridDev& g, const VxTri& t, int i, int j, uint32_t* stack) {
     const float cx = (float)i + 0.5f, cy = (float)j + 0.5f;
     const float w0 = vx_edge(t.qa[1], t.qb[1], t.qa[2], t.qb[2], cx, cy);
     const float w1 = vx_edge(t.qa[2], t.qb[2], t.qa[0], t.qb[0], cx, cy);
@@ -139,7 +142,17 @@ __device__ __forceinline__ bool vx_pixel(const VxScene& sc, const VxGridDev& g, 
             const f3 diffuse = mk3(L.Color[0], L.Color[1], L.Color[2]) * cosTheta * albedo;
             const float lr = fmaxf(L.Radius, 0.0001f);
             const float dsq = fmaxf(dist * dist, 0.0001f);
-            direct = direct + diffuse * ((lr * lr) / dsq);
+            f3 contrib = diffuse * ((lr * lr) / dsq);
+            if (L.PointShadowIndex >= 0 && sc.occValid) {
+                // Visibility(pointShadow, -sampleToLight) (fragment.glsl:100-110): the shadow-map compare point sits 2 % of the way
+                // towards the light; here that point is connected to the light by an any-hit ray instead of the PCF lookup
+                const float bias = 0.02f;
+                HitRec sh;
+                uint32_t sx;
+                const bool occluded = trace_any(sc.occ, fragPos + sampleToLight * bias, lightDir, dist * (1.0f - bias), false, stack, sh, sx);
+                contrib = contrib * (occluded ? 0.0f : 1.0f);
+            }
+            direct = direct + contrib;
         }
     }
     direct = direct + albedo * 0.02f;
@@ -175,6 +188,8 @@ struct VxVoxelizeArgs {
 };
 
 __global__ void __launch_bounds__(256) k_vx_voxelize_small(VxVoxelizeArgs a) {
+    extern __shared__ uint32_t s_vxStack[];          // shadow-ray traversal stacks (only with point-shadowed lights)
+    uint32_t* stack = s_vxStack + threadIdx.x;
     const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
     uint32_t frags = 0;
     if (k < a.triCount) {
@@ -184,7 +199,7 @@ __global__ void __launch_bounds__(256) k_vx_voxelize_small(VxVoxelizeArgs a) {
             const int area = (t.i1 - t.i0 + 1) * (t.j1 - t.j0 + 1);
             if (area <= IDKVX_SMALL_LIMIT) {
                 for (int j = t.j0; j <= t.j1; j++)
-                    for (int i = t.i0; i <= t.i1; i++) frags += vx_pixel(a.sc, a.g, t, i, j) ? 1u : 0u;
+                    for (int i = t.i0; i <= t.i1; i++) frags += vx_pixel(a.sc, a.g, t, i, j, stack) ? 1u : 0u;
             } else {
                 // cut the bounding box into tiles and queue one work item per tile (a wall-sized triangle becomes
                 // dozens of CTAs instead of one); if the queue is full the thread rasterises the remainder itself
@@ -197,7 +212,7 @@ __global__ void __launch_bounds__(256) k_vx_voxelize_small(VxVoxelizeArgs a) {
                     } else {
                         const int i0 = t.i0 + ox * IDKVX_TILE, j0 = t.j0 + oy * IDKVX_TILE;
                         for (int j = j0; j <= min(t.j1, j0 + IDKVX_TILE - 1); j++)
-                            for (int i = i0; i <= min(t.i1, i0 + IDKVX_TILE - 1); i++) frags += vx_pixel(a.sc, a.g, t, i, j) ? 1u : 0u;
+                            for (int i = i0; i <= min(t.i1, i0 + IDKVX_TILE - 1); i++) frags += vx_pixel(a.sc, a.g, t, i, j, stack) ? 1u : 0u;
                     }
                 }
             }
@@ -211,6 +226,8 @@ __global__ void __launch_bounds__(256) k_vx_voxelize_small(VxVoxelizeArgs a) {
 __global__ void __launch_bounds__(256) k_vx_voxelize_large(VxScene sc, VxGridDev g, const uint4* __restrict__ queue,
                                                            const uint32_t* __restrict__ queueCount, uint32_t queueCapacity,
                                                            unsigned long long* fragments) {
+    extern __shared__ uint32_t s_vxStack[];
+    uint32_t* stack = s_vxStack + threadIdx.x;
     const uint32_t n = min(*queueCount, queueCapacity);
     uint32_t frags = 0;
     for (uint32_t q = blockIdx.x; q < n; q += gridDim.x) {
@@ -220,7 +237,7 @@ __global__ void __launch_bounds__(256) k_vx_voxelize_large(VxScene sc, VxGridDev
         const int i0 = t.i0 + (int)e.z * IDKVX_TILE, j0 = t.j0 + (int)e.w * IDKVX_TILE;
         const int w = min(t.i1, i0 + IDKVX_TILE - 1) - i0 + 1, h = min(t.j1, j0 + IDKVX_TILE - 1) - j0 + 1;
         for (int p = threadIdx.x; p < w * h; p += blockDim.x)
-            frags += vx_pixel(sc, g, t, i0 + p % w, j0 + p / w) ? 1u : 0u;
+            frags += vx_pixel(sc, g, t, i0 + p % w, j0 + p / w, stack) ? 1u : 0u;
     }
     for (int off = 16; off > 0; off >>= 1) frags += __shfl_down_sync(0xffffffffu, frags, off);
     if ((threadIdx.x & 31) == 0 && frags) atomicAdd(fragments, (unsigned long long)frags);

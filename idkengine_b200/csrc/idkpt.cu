@@ -1778,3 +1778,5 @@ static int trace_rays_impl(IdkPtCtx* ctx, const IdkPtRay* rays, uint64_t count, 
 }
 
 } // extern "C"
+
+#include "idkvx_impl.cuh"

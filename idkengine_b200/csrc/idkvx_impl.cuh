@@ -1,4 +1,5 @@
-// libidkpt, VXGI part: C ABI of include/idkvx.h over the kernels of idk_vxgi.cuh.
+// libidkpt, VXGI part: C ABI of include/idkvx.h over the kernels of idk_vxgi.cuh. Included at the end of idkpt.cu (one
+// translation unit), so that the voxeliser can trace shadow rays through the path tracer's device scene (idk_shadows.cuh).
 // Host sequencing mirrors Voxelizer.Render (IDKEngine/Source/Render/VXGI/Voxelizer/Voxelizer.cs:109-228:
 // ClearTextures -> Voxelize -> Mipmap levels 1..n-1) and ConeTracer.Compute (ConeTracing/ConeTracer.cs:37-50).
 #include <cuda_runtime.h>
@@ -11,6 +12,7 @@
 #include "../../include/idkvx.h"
 #include "idk_vxgi.cuh"
 #include "idk_textures_host.h"
+#pragma once
 
 static thread_local std::string g_vxCreateError;
 
@@ -31,6 +33,8 @@ struct IdkVxCtx {
     void* dTexPixels = nullptr; void* dTexRecs = nullptr; void* dSrgbLut = nullptr;
     void* dQueue = nullptr; void* dQueueCount = nullptr; void* dCounters = nullptr;
     size_t queueCapacity = 0;
+    IdkPtCtx* shadowTracer = nullptr;     // idkvx_set_shadow_tracer: visibility of point-shadowed lights by shadow rays through this scene
+    bool shadowedLights = false;
 };
 
 #define VCK(call)                                                                                  \
@@ -139,8 +143,8 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
     if (!s->BlasTriangles || !s->BlasDescs || !s->BlasInstances || !s->MeshTransforms || !s->Meshes || !s->Materials || !s->Vertices || !s->VertexPositions)
         return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_set_scene: a required array is null");
     if (s->LightCount > IDK_GPU_MAX_UBO_LIGHT_COUNT) return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_set_scene: more than 256 lights");
-    for (uint64_t i = 0; i < s->LightCount; i++)
-        if (s->Lights[i].PointShadowIndex >= 0) return vfail(ctx, IDKPT_ERR_UNSUPPORTED, "idkvx_set_scene: point-shadowed lights are not supported (PointShadowIndex must be -1)");
+    bool shadowed = false;
+    for (uint64_t i = 0; i < s->LightCount; i++) shadowed = shadowed || s->Lights[i].PointShadowIndex >= 0;
     for (uint64_t i = 0; i < s->BlasInstanceCount; i++)
         if (s->BlasInstances[i].BlasId >= s->BlasDescCount || s->BlasInstances[i].MeshTransformId >= s->MeshTransformCount)
             return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_set_scene: BlasInstance references a missing BLAS or transform");
@@ -205,6 +209,7 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
     sc.srgbLut = (const float*)ctx->dSrgbLut;
     sc.lightCount = (uint32_t)s->LightCount;
     ctx->counts = *s;
+    ctx->shadowedLights = shadowed;
     VCK(cudaStreamSynchronize(ctx->stream));
     ctx->haveScene = true;
     return IDKPT_OK;
@@ -213,6 +218,23 @@ IDKPT_API int idkvx_set_scene(IdkVxCtx* ctx, const IdkPtSceneDesc* s) {
 IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats) {
     if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
     if (!ctx->haveScene) return vfail(ctx, IDKPT_ERR_NO_SCENE, "idkvx_voxelize: idkvx_set_scene has not been called");
+    // fragment.glsl:55-58: lights with PointShadowIndex >= 0 are multiplied by Visibility(), a PCF lookup into the shadow cube
+    // map the rasteriser renders. Without a rasteriser the same question -- is the (2 % biased) sample point visible from the
+    // light -- is answered by an any-hit shadow ray through the path tracer's BVH (idkvx_set_shadow_tracer).
+    size_t shadowSmem = 0;
+    ctx->sc.occValid = 0;
+    if (ctx->shadowedLights) {
+        IdkPtCtx* pt = ctx->shadowTracer;
+        if (!pt || !pt->haveScene || pt->device != ctx->device)
+            return vfail(ctx, IDKPT_ERR_UNSUPPORTED, "idkvx_voxelize: the scene has point-shadowed lights (PointShadowIndex >= 0): give the voxeliser a path-tracer context "
+                                                     "with the same scene on the same device (idkvx_set_shadow_tracer) to trace their visibility");
+        if (pt->asyncPending) { cudaSetDevice(pt->device); drain(pt); }
+        ctx->sc.occ = pt->sc;
+        ctx->sc.occValid = 1;
+        shadowSmem = pt->stackBytes;
+        VCK(cudaFuncSetAttribute(k_vx_voxelize_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadowSmem));
+        VCK(cudaFuncSetAttribute(k_vx_voxelize_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)shadowSmem));
+    }
     VCK(cudaSetDevice(ctx->device));
     if (stats) memset(stats, 0, sizeof(*stats));
     cudaEvent_t ev[4];
@@ -232,10 +254,10 @@ IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats) {
         a.triFirst = (uint32_t)d.TriangleOffset; a.triCount = (uint32_t)d.TriangleCount;
         a.queue = (uint4*)ctx->dQueue; a.queueCount = (uint32_t*)ctx->dQueueCount; a.queueCapacity = (uint32_t)ctx->queueCapacity;
         a.fragments = (unsigned long long*)ctx->dCounters;
-        k_vx_voxelize_small<<<(a.triCount + 255) / 256, 256, 0, ctx->stream>>>(a);
+        k_vx_voxelize_small<<<(a.triCount + 255) / 256, 256, shadowSmem, ctx->stream>>>(a);
         launches++;
     }
-    k_vx_voxelize_large<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->sc, ctx->grid, (const uint4*)ctx->dQueue, (const uint32_t*)ctx->dQueueCount,
+    k_vx_voxelize_large<<<ctx->smCount * 8, 256, shadowSmem, ctx->stream>>>(ctx->sc, ctx->grid, (const uint4*)ctx->dQueue, (const uint32_t*)ctx->dQueueCount,
                                                                      (uint32_t)ctx->queueCapacity, (unsigned long long*)ctx->dCounters);
     launches++;
     VCK(cudaEventRecord(ev[2], ctx->stream));
@@ -270,6 +292,12 @@ IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats) {
         stats->KernelLaunches = launches;
     }
     for (auto& e : ev) cudaEventDestroy(e);
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkvx_set_shadow_tracer(IdkVxCtx* ctx, IdkPtCtx* pathTracer) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    ctx->shadowTracer = pathTracer;
     return IDKPT_OK;
 }
 

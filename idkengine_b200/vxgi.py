@@ -25,7 +25,7 @@ class IdkVxStats(ctypes.Structure):
 
 
 VX_EXPORTS = ["idkvx_create", "idkvx_destroy", "idkvx_last_error", "idkvx_set_scene", "idkvx_set_grid", "idkvx_level_count",
-              "idkvx_voxelize", "idkvx_read_level", "idkvx_cone_trace"]
+              "idkvx_voxelize", "idkvx_read_level", "idkvx_cone_trace", "idkvx_set_shadow_tracer"]
 
 DEFAULT_GRID_MIN = (-28.0, -3.0, -17.0)   # RasterPipeline.cs:213
 DEFAULT_GRID_MAX = (28.0, 20.0, 17.0)
@@ -68,6 +68,8 @@ def _declare(L):
     L.idkvx_level_count.argtypes = [c_vp]
     L.idkvx_voxelize.restype = c_i32
     L.idkvx_voxelize.argtypes = [c_vp, P(IdkVxStats)]
+    L.idkvx_set_shadow_tracer.restype = c_i32
+    L.idkvx_set_shadow_tracer.argtypes = [c_vp, c_vp]
     L.idkvx_read_level.restype = c_i32
     L.idkvx_read_level.argtypes = [c_vp, c_i32, c_vp, c_u64]
     L.idkvx_cone_trace.restype = c_i32
@@ -107,6 +109,10 @@ class Voxelizer:
     def SetScene(self, scene):
         d, keep = capi.scene_desc(scene)
         self._check(self._lib.idkvx_set_scene(self._ctx, ctypes.byref(d)), "idkvx_set_scene")
+
+    def SetShadowTracer(self, path_tracer):
+        """Shadow rays for lights with PointShadowIndex >= 0 go through this PathTracer's scene (None detaches)."""
+        self._check(self._lib.idkvx_set_shadow_tracer(self._ctx, path_tracer._ctx if path_tracer is not None else None), "idkvx_set_shadow_tracer")
 
     def Render(self):
         """Voxelizer.Render(modelManager): clear + voxelise + mipmap."""

@@ -67,6 +67,13 @@ IDKPT_API int32_t idkvx_level_count(IdkVxCtx* ctx);                             
 IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats);
 
 /* rgba16f texels of one mip level, x fastest (size = w*h*d*8 bytes). */
+/* Lights with PointShadowIndex >= 0 are attenuated by Visibility() in the fragment stage (Voxelize/fragment.glsl:55-58,100-115),
+ * a PCF lookup into the shadow cube map the rasteriser renders (PointShadowManager). Without a rasteriser the voxeliser asks the
+ * same question with an any-hit shadow ray from the 2 %-biased sample point to the light through the BVH of a path-tracer
+ * context holding the same scene on the same device (hard shadows instead of the PCF-filtered lookup). NULL detaches.
+ * A scene with such lights cannot be voxelised without it (IDKPT_ERR_UNSUPPORTED). */
+struct IdkPtCtx;
+IDKPT_API int idkvx_set_shadow_tracer(IdkVxCtx* ctx, struct IdkPtCtx* path_tracer);
 IDKPT_API int idkvx_read_level(IdkVxCtx* ctx, int32_t level, void* dst_rgba16f, uint64_t bytes);
 
 /* ConeTracer.Compute(): per pixel of a width x height G-buffer (host arrays: depth [w*h], normal = octahedral rg

@@ -111,8 +111,46 @@ def test_gpu_vxgi_errors():
         with pytest.raises(vxgi.IdkVxError, match="idkvx_set_scene has not been called"):
             vx.Render()
         scene.lights["PointShadowIndex"][0] = 0
+        vx.SetScene(scene)                                     # accepted ...
         with pytest.raises(vxgi.IdkVxError, match="point-shadowed"):
-            vx.SetScene(scene)
+            vx.Render()                                        # ... but needs a shadow tracer to evaluate Visibility()
+
+
+def test_oracle_point_shadowed_light_darkens_occluded_voxels():
+    """fragment.glsl:55-58: a light with PointShadowIndex >= 0 is multiplied by Visibility(). With the shadow-ray substitute the
+    voxels behind the tall box (seen from the light) lose that light's contribution; lit voxels keep it exactly."""
+    scene, cam = lit_cornell()
+    ci = vxgi.create_info(48, GRID_MIN, GRID_MAX)
+    plain = ol.vx_voxelize(scene, ci)[0][0].astype(np.float32)
+    scene.lights["PointShadowIndex"][:] = [0, 1]
+    shadowed = ol.vx_voxelize(scene, ci)[0][0].astype(np.float32)
+    assert np.array_equal(plain[..., 3], shadowed[..., 3])                    # same coverage
+    assert (shadowed[..., :3] <= plain[..., :3]).all()
+    darker = (shadowed[..., :3] < plain[..., :3]).any(-1)
+    occ = plain[..., 3] == 1.0
+    assert 0.02 < darker.sum() / occ.sum() < 0.9                              # some voxels are in shadow, many are not
+    same = occ & ~darker
+    assert np.array_equal(shadowed[same], plain[same])
+
+
+@pytest.mark.gpu
+def test_gpu_point_shadowed_lights_match_oracle():
+    from idkengine_b200.pathtracer import PathTracer
+    scene, cam = lit_cornell()
+    scene.lights["PointShadowIndex"][:] = [0, 1]
+    ci = vxgi.create_info((48, 40, 44), GRID_MIN, GRID_MAX)
+    levels, raw, frags = ol.vx_voxelize(scene, ci)
+    with PathTracer(32, 32) as pt, vxgi.Voxelizer((48, 40, 44), GRID_MIN, GRID_MAX) as vx:
+        pt.SetScene(scene)
+        vx.SetScene(scene)
+        vx.SetShadowTracer(pt)
+        s = vx.Render()
+        assert s.Fragments == frags
+        for l, lv in enumerate(levels):
+            assert np.array_equal(vx.ReadLevel(l).view(np.uint16), lv.view(np.uint16)), f"level {l}"
+        vx.SetShadowTracer(None)
+        with pytest.raises(vxgi.IdkVxError, match="point-shadowed"):
+            vx.Render()
 
 
 # ---- material textures in the voxeliser (BaseColor / Emissive slots, base level, same sampler rules as the path tracer)
