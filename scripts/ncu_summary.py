@@ -86,5 +86,43 @@ def full(path):
             print(f"{name:84s} [{units[i]:12s}] " + "  ".join(r[i] for r in rows[2:]))
 
 
+def raw_rows(path):
+    out = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr = rows[0]
+    return [dict(zip(hdr, r)) for r in rows[2:]]
+
+
+def traffic(trav_rep, shade_rep, out_json):
+    """profiles/traffic.json, read by bench.py: DRAM bytes per launch and DRAM utilisation of the captured traversal launches
+    (mean over the capture) and of the shade kernel -- regenerated from THIS round's captures, never carried over."""
+    import json
+
+    def num(r, k):
+        return float(r[k].replace(",", ""))
+    t = raw_rows(trav_rep)
+    s_ = raw_rows(shade_rep)
+    dram = [num(r, "dram__bytes_read.sum") + num(r, "dram__bytes_write.sum") for r in t]
+    unit = {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}
+    rows = list(csv.reader(subprocess.run(["ncu", "-i", trav_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout.splitlines()))
+    u = unit[rows[1][rows[0].index("dram__bytes_read.sum")]]
+    doc = {
+        "kernel": t[0]["Kernel Name"],
+        "dram_bytes_per_launch": sum(dram) / len(dram) * u,
+        "dram_frac": sum(num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") for r in t) / len(t) / 100.0,
+        "l1tex_throughput_frac": sum(num(r, "l1tex__throughput.avg.pct_of_peak_sustained_elapsed") for r in t) / len(t) / 100.0,
+        "issue_active_frac": sum(num(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") for r in t) / len(t) / 100.0,
+        "active_lanes_per_instruction": sum(num(r, "smsp__thread_inst_executed_per_inst_executed.ratio") for r in t) / len(t),
+        "shade_dram_frac": sum(num(r, "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed") for r in s_) / len(s_) / 100.0,
+        "launches_captured": len(t),
+        "source": f"{trav_rep} / {shade_rep}: ncu --set full --clock-control none (scripts/gpu_session.sh ncu), bench workload, sample 2, bounces 1-3",
+    }
+    json.dump(doc, open(out_json, "w"), indent=1)
+    print(json.dumps(doc, indent=1))
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3], sys.argv[4])
+    else:
+        {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2])
