@@ -20,6 +20,9 @@ for s in $steps; do
        timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_compact -s 8 -c 2 -f -o gpurun_out/prof_compact_r02 python scripts/ncu_target.py pt > gpurun_out/ncu_compact.log 2>&1
        timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_vx_ -c 14 -f -o gpurun_out/prof_vxgi_r02 python scripts/ncu_target.py vxgi > gpurun_out/ncu_vx.log 2>&1
        ls -la gpurun_out/*.ncu-rep; tail -2 gpurun_out/ncu_t2.log;;
+    sanitize) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitize_memcheck.log; tail -6 gpurun_out/sanitize_memcheck.log
+       timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/sanitize.py > gpurun_out/sanitize_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/sanitize_racecheck.log; tail -4 gpurun_out/sanitize_racecheck.log;;
+    smoke) timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -3;;
     *) echo "unknown step $s";;
   esac
 done

@@ -54,6 +54,48 @@ with PathTracer(64, 48) as pt:
     pt.Compute()
 print("dynamic ok")
 
+# round 2 additions: TLAS walk inside k_traverse2 (async lanes), BC7 / BC5 / BC4 decode at upload, float textures, cube-map sky
+# with seamless filtering, denoise hand-off, point-shadowed lights in the voxeliser
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests"))
+import copy
+import bcn_ref
+scene3, cam3 = scenes.instance_grid(2, threads=1)
+with PathTracer(80, 56, lanes=3) as pt:
+    pt.SetScene(scene3); pt.SetFrame(scenes.camera_frame(cam3, 80, 56))
+    rng = np.random.default_rng(3)
+    pt.SetSky((0, 0, 0), rng.uniform(0, 2, (6, 8, 8, 4)).astype(np.float32))
+    pt.Compute()
+    for _ in range(3):
+        pt.ComputeAsync()
+    pt.Sync()
+print("tlas phase + cube sky ok")
+comp = copy.copy(scene)
+comp.textures = []
+rng = np.random.default_rng(4)
+for k, t in enumerate(scene.textures):
+    px = t["pixels"]; hh, ww = px.shape[:2]
+    nb = ((hh + 3) // 4) * ((ww + 3) // 4)
+    common = dict(wrap_s=t["wrap_s"], wrap_t=t["wrap_t"])
+    if k % 3 == 0:
+        comp.textures.append(dict(format=capi.IDKPT_TEX_BC7_SRGB, width=ww, height=hh, data=rng.integers(0, 256, (nb, 16), dtype=np.uint8), **common))
+    elif k % 3 == 1:
+        comp.textures.append(dict(format=capi.IDKPT_TEX_BC5_RG_UNORM, width=ww, height=hh, data=rng.integers(0, 256, (nb, 16), dtype=np.uint8), **common))
+    else:
+        comp.textures.append(dict(format=capi.IDKPT_TEX_BC4_R_UNORM, width=ww, height=hh, data=rng.integers(0, 256, (nb, 8), dtype=np.uint8), flags=0, **common))
+comp.textures[1] = dict(format=capi.IDKPT_TEX_RGBA32F, width=5, height=3, data=rng.uniform(0, 1, (3, 5, 4)).astype(np.float32), wrap_s=33071, wrap_t=33648, flags=1)
+s2 = capi.default_settings(); s2.OutputAOVs = 1
+with PathTracer(w, h, s2) as pt:
+    pt.SetScene(comp); pt.SetSky((0.6, 0.7, 0.9)); pt.SetFrame(frame)
+    pt.Compute(); pt.Compute()
+    pt.Denoise()
+    pt.PostProcess(source=capi.IDKPT_IMAGE_DENOISED)
+    pt.DenoiseDevicePtrs(); pt.DenoiseImportOutput()
+    shadowed = copy.copy(comp)
+    shadowed.lights = comp.lights.copy(); shadowed.lights["PointShadowIndex"][:] = 0
+    with vxgi.Voxelizer((20, 16, 24), (-3.1, -0.1, -3.1), (3.1, 4.1, 3.1)) as vx:
+        vx.SetScene(shadowed); vx.SetShadowTracer(pt); vx.Render()
+print("bcn + denoise + point shadows ok")
+
 with vxgi.Voxelizer((24, 20, 28), (-3.1, -0.1, -3.1), (3.1, 4.1, 3.1)) as vx:
     vx.SetScene(scene)
     vx.Render()
