@@ -21,6 +21,7 @@ struct VxGridDev {
     int sx[IDKVX_MAX_LEVELS], sy[IDKVX_MAX_LEVELS], sz[IDKVX_MAX_LEVELS];
     int levels;
     float gmin[3], gmax[3];
+    int z0, z1;                                    // voxelise only z in [z0, z1) (multi-GPU z-slab split; whole grid: 0, sz[0])
 };
 
 struct VxScene {
@@ -113,6 +114,7 @@ __device__ __forceinline__ bool vx_pixel(const VxScene& sc, const VxGridDev& g, 
     if (!(fu >= 0.0f && fv >= 0.0f && fw >= 0.0f)) return false;
     const int vx = (int)(fu * (float)g.sx[0]), vy = (int)(fv * (float)g.sy[0]), vz = (int)(fw * (float)g.sz[0]);
     if (vx >= g.sx[0] || vy >= g.sy[0] || vz >= g.sz[0]) return false;
+    if (vz < g.z0 || vz >= g.z1) return false;                    // another rank's slab
 
     // fragment.glsl:31-79 (no point shadows). GetSurface(material, TexCoord): the fragment stage samples with implicit
     // derivatives / mip levels; here the base level is sampled bilinearly like everywhere else in this library.
@@ -382,7 +384,8 @@ struct VxConeArgs {
     const float2* normalRG;
     const float2* metalRough;
     float4* out;
-    int width, height;
+    int width, height;            // height = rows in this launch's arrays
+    int fullHeight, rowFirst;     // the G-buffer's real height and the first row these arrays hold (screen-tiled cone tracing)
     unsigned long long* steps;
 };
 
@@ -421,15 +424,16 @@ __device__ __forceinline__ float4 vx_trace_cone(const VxGridDev& g, f3 origin, f
 }
 
 __global__ void __launch_bounds__(64) k_vx_cone_trace(VxConeArgs a) {
-    const int x = blockIdx.x * 8 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+    const int x = blockIdx.x * 8 + threadIdx.x, yl = blockIdx.y * 8 + threadIdx.y;
+    const int y = yl + a.rowFirst;
     uint32_t steps = 0;
-    if (x < a.width && y < a.height) {
-        const size_t p = (size_t)y * a.width + x;
+    if (x < a.width && yl < a.height) {
+        const size_t p = (size_t)yl * a.width + x;
         const float d = a.depth[p];
         if (d == 1.0f) {
             a.out[p] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         } else {
-            const float u = ((float)x + 0.5f) / (float)a.width, v = ((float)y + 0.5f) / (float)a.height;
+            const float u = ((float)x + 0.5f) / (float)a.width, v = ((float)y + 0.5f) / (float)a.fullHeight;
             const float nx = u * 2.0f - 1.0f, ny = v * 2.0f - 1.0f;
             const float* m = a.invProjView;
             const float wx = ((m[0] * nx + m[4] * ny) + m[8] * d) + m[12] * 1.0f;

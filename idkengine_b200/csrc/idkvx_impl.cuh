@@ -33,6 +33,7 @@ struct IdkVxCtx {
     void* dTexPixels = nullptr; void* dTexRecs = nullptr; void* dSrgbLut = nullptr;
     void* dQueue = nullptr; void* dQueueCount = nullptr; void* dCounters = nullptr;
     size_t queueCapacity = 0;
+    bool slabMode = false;                // idkvx_set_slab: voxelise one z-slab, no mip chain (the host all-gathers the slabs first)
     IdkPtCtx* shadowTracer = nullptr;     // idkvx_set_shadow_tracer: visibility of point-shadowed lights by shadow rays through this scene
     bool shadowedLights = false;
 };
@@ -95,6 +96,7 @@ IDKPT_API int idkvx_create(const IdkVxCreateInfo* ci, IdkVxCtx** out) {
     int levels = 1;
     while ((mx >> levels) > 0) levels++;
     ctx->grid.levels = levels;
+    ctx->grid.z0 = 0; ctx->grid.z1 = ci->Depth;
     size_t total = 0;
     for (int l = 0; l < levels; l++) {
         ctx->grid.sx[l] = std::max(1, ci->Width >> l);
@@ -261,7 +263,7 @@ IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats) {
                                                                      (uint32_t)ctx->queueCapacity, (unsigned long long*)ctx->dCounters);
     launches++;
     VCK(cudaEventRecord(ev[2], ctx->stream));
-    for (int l = 1; l < ctx->grid.levels; l++) {
+    for (int l = 1; l < (ctx->slabMode ? 1 : ctx->grid.levels); l++) {
         const size_t n = ctx->levelTexels[l];
         const int blocks = (int)std::min<size_t>((n + 255) / 256, (size_t)ctx->smCount * 16);
         // levels that halve exactly on every axis and are big enough to fill the machine take the shared-memory tiled kernel
@@ -295,6 +297,46 @@ IDKPT_API int idkvx_voxelize(IdkVxCtx* ctx, IdkVxStats* stats) {
     return IDKPT_OK;
 }
 
+// ---- multi-GPU: voxelise by z-slab, all-gather the slabs, then build the mip chain on every rank -------------------
+IDKPT_API int idkvx_set_slab(IdkVxCtx* ctx, int32_t z0, int32_t z1) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    const int d = ctx->grid.sz[0];
+    if (z0 < 0 || z1 > d || z0 >= z1) return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_set_slab: need 0 <= z0 < z1 <= depth");
+    ctx->grid.z0 = z0; ctx->grid.z1 = z1;
+    ctx->slabMode = !(z0 == 0 && z1 == d);
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkvx_level_device_ptr(IdkVxCtx* ctx, int32_t level, void** devPtr, uint64_t* bytes) {
+    if (!ctx || !devPtr) return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_level_device_ptr: null argument");
+    if (level < 0 || level >= ctx->grid.levels) return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_level_device_ptr: level out of range");
+    *devPtr = ctx->grid.level[level];
+    if (bytes) *bytes = ctx->levelTexels[level] * 8;
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkvx_mipmap(IdkVxCtx* ctx, IdkVxStats* stats) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    VCK(cudaSetDevice(ctx->device));
+    if (stats) memset(stats, 0, sizeof(*stats));
+    cudaEvent_t e0, e1;
+    VCK(cudaEventCreate(&e0)); VCK(cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->stream);
+    uint32_t launches = 0;
+    for (int l = 1; l < ctx->grid.levels; l++) {
+        const size_t n = ctx->levelTexels[l];
+        k_vx_mipmap<<<(int)std::min<size_t>((n + 255) / 256, (size_t)ctx->smCount * 16), 256, 0, ctx->stream>>>(ctx->grid, l);
+        launches++;
+    }
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && stats) { cudaEventElapsedTime(&stats->MipmapMs, e0, e1); stats->KernelLaunches = launches; }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) { ctx->lastError = std::string("idkvx_mipmap: ") + cudaGetErrorString(e); return IDKPT_ERR_CUDA; }
+    return IDKPT_OK;
+}
+
 IDKPT_API int idkvx_set_shadow_tracer(IdkVxCtx* ctx, IdkPtCtx* pathTracer) {
     if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
     ctx->shadowTracer = pathTracer;
@@ -311,11 +353,23 @@ IDKPT_API int idkvx_read_level(IdkVxCtx* ctx, int32_t level, void* dst, uint64_t
     return IDKPT_OK;
 }
 
+IDKPT_API int idkvx_cone_trace_rows(IdkVxCtx* ctx, const GpuPerFrameData* frame, const IdkVxConeSettings* st, const float* depth,
+                                    const float* normalRG, const float* metallicRoughness, int32_t width, int32_t fullHeight,
+                                    int32_t rowFirst, int32_t height, const float skyColor[3], float* out, IdkVxStats* stats);
+
 IDKPT_API int idkvx_cone_trace(IdkVxCtx* ctx, const GpuPerFrameData* frame, const IdkVxConeSettings* st, const float* depth,
                                const float* normalRG, const float* metallicRoughness, int32_t width, int32_t height,
                                const float skyColor[3], float* out, IdkVxStats* stats) {
+    return idkvx_cone_trace_rows(ctx, frame, st, depth, normalRG, metallicRoughness, width, height, 0, height, skyColor, out, stats);
+}
+
+// Screen-tiled cone tracing (multi-GPU: the grid is replicated, every rank traces its rows): the arrays hold `height` rows starting
+// at row `rowFirst` of a G-buffer that is `fullHeight` rows tall; pixel coordinates (noise, NDC) are those of the full image.
+IDKPT_API int idkvx_cone_trace_rows(IdkVxCtx* ctx, const GpuPerFrameData* frame, const IdkVxConeSettings* st, const float* depth,
+                                    const float* normalRG, const float* metallicRoughness, int32_t width, int32_t fullHeight,
+                                    int32_t rowFirst, int32_t height, const float skyColor[3], float* out, IdkVxStats* stats) {
     if (!ctx || !frame || !st || !depth || !normalRG || !metallicRoughness || !skyColor || !out) return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_cone_trace: null argument");
-    if (width < 1 || height < 1 || width > 16384 || height > 16384) return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_cone_trace: invalid image size");
+    if (width < 1 || height < 1 || width > 16384 || fullHeight > 16384 || rowFirst < 0 || rowFirst + height > fullHeight) return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_cone_trace: invalid image size / row range");
     if (st->MaxSamples < 1 || st->MaxSamples > 64) return vfail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkvx_cone_trace: MaxSamples out of range");
     VCK(cudaSetDevice(ctx->device));
     if (stats) memset(stats, 0, sizeof(*stats));
@@ -340,7 +394,7 @@ IDKPT_API int idkvx_cone_trace(IdkVxCtx* ctx, const GpuPerFrameData* frame, cons
         a.normalRayOffset = st->NormalRayOffset; a.noiseIndex = st->NoiseIndex;
         for (int i = 0; i < 3; i++) a.sky[i] = skyColor[i];
         a.depth = (const float*)dDepth; a.normalRG = (const float2*)dN; a.metalRough = (const float2*)dMR; a.out = (float4*)dOut;
-        a.width = width; a.height = height; a.steps = (unsigned long long*)ctx->dCounters;
+        a.width = width; a.height = height; a.fullHeight = fullHeight; a.rowFirst = rowFirst; a.steps = (unsigned long long*)ctx->dCounters;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
         cudaEventRecord(e0, ctx->stream);
         k_vx_cone_trace<<<dim3((width + 7) / 8, (height + 7) / 8), dim3(8, 8), 0, ctx->stream>>>(a);

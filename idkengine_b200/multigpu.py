@@ -64,3 +64,39 @@ class DeviceArray:
 
     def __init__(self, ptr, shape, typestr="<f4"):
         self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+# ---- VXGI over N GPUs: z-slab voxelisation + ONE all-gather of the slabs, mip chain and cone tracing replicated / tiled
+def slab_range(depth, rank, world):
+    """z range of rank's slab: equal slabs when world divides depth, otherwise the last ranks get one layer less."""
+    base, extra = divmod(depth, world)
+    z0 = rank * base + min(rank, extra)
+    return z0, z0 + base + (1 if rank < extra else 0)
+
+
+def voxelize_multi_gpu(vx, rank, world, device, group=None):
+    """Voxelizer.Render() across `world` ranks: every rank voxelises its z-slab of level 0, the slabs are all-gathered straight
+    into every rank's grid (a slab of the linear x-fastest level is one contiguous range; NCCL all_gather_into_tensor, in place
+    when the slabs are equal), then every rank builds the mip chain. The merged grid equals the single-GPU grid bit for bit
+    (the voxel merge is a per-channel max). Returns (voxelise stats of this rank, mip stats)."""
+    import torch
+    import torch.distributed as dist
+    w, h, d = vx.sizes[0]
+    z0, z1 = slab_range(d, rank, world)
+    vx.SetSlab(z0, z1)
+    st = vx.Render()
+    ptr, nbytes = vx.LevelDevicePtr(0)
+    level0 = torch.as_tensor(DeviceArray(ptr, (d, h * w * 2), "<u4"), device=device)     # 8 bytes per texel as 2 x uint32
+    if world > 1:
+        if d % world == 0:
+            dist.all_gather_into_tensor(level0.view(-1), level0[z0:z1].reshape(-1), group=group)
+        else:
+            parts = [torch.empty((slab_range(d, r, world)[1] - slab_range(d, r, world)[0], h * w * 2), dtype=level0.dtype, device=device) for r in range(world)]
+            dist.all_gather(parts, level0[z0:z1].contiguous(), group=group)
+            for r, part in enumerate(parts):
+                a, b = slab_range(d, r, world)
+                level0[a:b].copy_(part)
+        torch.cuda.synchronize(device)
+    mst = vx.Mipmap()
+    vx.SetSlab(0, d)
+    return st, mst

@@ -25,7 +25,8 @@ class IdkVxStats(ctypes.Structure):
 
 
 VX_EXPORTS = ["idkvx_create", "idkvx_destroy", "idkvx_last_error", "idkvx_set_scene", "idkvx_set_grid", "idkvx_level_count",
-              "idkvx_voxelize", "idkvx_read_level", "idkvx_cone_trace", "idkvx_set_shadow_tracer"]
+              "idkvx_voxelize", "idkvx_read_level", "idkvx_cone_trace", "idkvx_set_shadow_tracer",
+              "idkvx_set_slab", "idkvx_level_device_ptr", "idkvx_mipmap", "idkvx_cone_trace_rows"]
 
 DEFAULT_GRID_MIN = (-28.0, -3.0, -17.0)   # RasterPipeline.cs:213
 DEFAULT_GRID_MAX = (28.0, 20.0, 17.0)
@@ -68,6 +69,14 @@ def _declare(L):
     L.idkvx_level_count.argtypes = [c_vp]
     L.idkvx_voxelize.restype = c_i32
     L.idkvx_voxelize.argtypes = [c_vp, P(IdkVxStats)]
+    L.idkvx_set_slab.restype = c_i32
+    L.idkvx_set_slab.argtypes = [c_vp, c_i32, c_i32]
+    L.idkvx_level_device_ptr.restype = c_i32
+    L.idkvx_level_device_ptr.argtypes = [c_vp, c_i32, P(c_vp), P(c_u64)]
+    L.idkvx_mipmap.restype = c_i32
+    L.idkvx_mipmap.argtypes = [c_vp, P(IdkVxStats)]
+    L.idkvx_cone_trace_rows.restype = c_i32
+    L.idkvx_cone_trace_rows.argtypes = [c_vp, c_vp, P(IdkVxConeSettings), c_vp, c_vp, c_vp, c_i32, c_i32, c_i32, c_i32, P(c_f * 3), c_vp, P(IdkVxStats)]
     L.idkvx_set_shadow_tracer.restype = c_i32
     L.idkvx_set_shadow_tracer.argtypes = [c_vp, c_vp]
     L.idkvx_read_level.restype = c_i32
@@ -113,6 +122,35 @@ class Voxelizer:
     def SetShadowTracer(self, path_tracer):
         """Shadow rays for lights with PointShadowIndex >= 0 go through this PathTracer's scene (None detaches)."""
         self._check(self._lib.idkvx_set_shadow_tracer(self._ctx, path_tracer._ctx if path_tracer is not None else None), "idkvx_set_shadow_tracer")
+
+    # ---- multi-GPU: z-slab voxelisation, gather, mip chain, screen-tiled cone trace (include/idkvx.h)
+    def SetSlab(self, z0, z1):
+        self._check(self._lib.idkvx_set_slab(self._ctx, z0, z1), "idkvx_set_slab")
+
+    def LevelDevicePtr(self, level):
+        p, n = c_vp(), c_u64()
+        self._check(self._lib.idkvx_level_device_ptr(self._ctx, level, ctypes.byref(p), ctypes.byref(n)), "idkvx_level_device_ptr")
+        return p.value, n.value
+
+    def Mipmap(self):
+        st = IdkVxStats()
+        self._check(self._lib.idkvx_mipmap(self._ctx, ctypes.byref(st)), "idkvx_mipmap")
+        return st
+
+    def ConeTraceRows(self, frame, depth, normal_rg, metallic_roughness, full_height, row_first, settings=None, sky=(0.6, 0.7, 0.9)):
+        """ConeTracer.Compute on rows [row_first, row_first + depth.shape[0]) of a full_height-row G-buffer."""
+        settings = settings or default_cone_settings()
+        h, w = depth.shape
+        depth = np.ascontiguousarray(depth, np.float32)
+        nrg = np.ascontiguousarray(normal_rg, np.float32)
+        mr = np.ascontiguousarray(metallic_roughness, np.float32)
+        out = np.zeros((h, w, 4), np.float32)
+        st = IdkVxStats()
+        skyc = (c_f * 3)(*sky)
+        frame = np.ascontiguousarray(frame)
+        self._check(self._lib.idkvx_cone_trace_rows(self._ctx, frame.ctypes.data, ctypes.byref(settings), depth.ctypes.data, nrg.ctypes.data,
+                                                    mr.ctypes.data, w, full_height, row_first, h, ctypes.byref(skyc), out.ctypes.data, ctypes.byref(st)), "idkvx_cone_trace_rows")
+        return out, st
 
     def Render(self):
         """Voxelizer.Render(modelManager): clear + voxelise + mipmap."""

@@ -82,6 +82,20 @@ IDKPT_API int idkvx_cone_trace(IdkVxCtx* ctx, const GpuPerFrameData* frame, cons
                                const float* depth, const float* normalRG, const float* metallicRoughness,
                                int32_t width, int32_t height, const float skyColor[3], float* out_rgba32f, IdkVxStats* stats);
 
+/* ---- multi-GPU: voxelise by z-slab, all-gather, cone-trace screen tiles ----
+ * Rank r of N: idkvx_set_slab(r * D / N, (r + 1) * D / N), idkvx_voxelize (writes only that slab of level 0, no mip chain),
+ * one all-gather of the slabs straight into the grid (a z-slab of the linear x-fastest level is one contiguous range:
+ * idkvx_level_device_ptr(0) + z0 * W * H * 8; with equal slabs an in-place ncclAllGather), idkvx_mipmap on every rank, then
+ * idkvx_cone_trace_rows over the rank's rows of the G-buffer. The merge is max per channel, so the gathered grid equals the
+ * single-GPU grid bit for bit. idkvx_set_slab(0, D) returns to the single-GPU behaviour. */
+IDKPT_API int idkvx_set_slab(IdkVxCtx* ctx, int32_t z0, int32_t z1);
+IDKPT_API int idkvx_level_device_ptr(IdkVxCtx* ctx, int32_t level, void** dev_ptr, uint64_t* bytes);
+IDKPT_API int idkvx_mipmap(IdkVxCtx* ctx, IdkVxStats* stats);
+IDKPT_API int idkvx_cone_trace_rows(IdkVxCtx* ctx, const GpuPerFrameData* frame, const IdkVxConeSettings* settings,
+                                    const float* depth, const float* normalRG, const float* metallicRoughness,
+                                    int32_t width, int32_t full_height, int32_t row_first, int32_t row_count,
+                                    const float skyColor[3], float* out_rgba32f, IdkVxStats* stats);
+
 #ifdef __cplusplus
 }
 #endif

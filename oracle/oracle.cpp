@@ -1184,6 +1184,7 @@ ORACLE_API int oracle_path_trace(const IdkPtSceneDesc* scene, const IdkPtSkyDesc
 
         // ---- FirstHit (FirstHit/compute.glsl:44-98)
         parallel_for(nLocal, T, [&](size_t b, size_t e, int tid) {
+            uint64_t lS = 0, lT = 0, lI = 0, lH = 0;      // per-chunk sums: the per-worker slots share cache lines
             for (size_t li = b; li < e; li++) {
                 int x = (int)(li % (size_t)width), y = rows[li / (size_t)width];
                 uint32_t unsw = swzInv[(size_t)(y / 8) * ngx + (size_t)(x / 8)];
@@ -1212,8 +1213,9 @@ ORACLE_API int oracle_path_trace(const IdkPtSceneDesc* scene, const IdkPtSkyDesc
                 uint32_t key; RayStats rs;
                 bool c = ShadeTraceRay(s, st, rng, r, a, true, gidX, gidY, key, rs);
                 rays[li] = r; aovs[li] = a; cont[li] = c ? 1 : 0;
-                accS[tid] += rs.steps; accT[tid] += rs.tris; accI[tid] += rs.instances; accH[tid] += rs.hitGeometry ? 1 : 0;
+                lS += rs.steps; lT += rs.tris; lI += rs.instances; lH += rs.hitGeometry ? 1 : 0;
             }
+            accS[tid] += lS; accT[tid] += lT; accI[tid] += lI; accH[tid] += lH;
         });
         alive.clear();
         for (size_t li = 0; li < nLocal; li++) if (cont[li]) alive.push_back((uint32_t)li);
@@ -1235,6 +1237,7 @@ ORACLE_API int oracle_path_trace(const IdkPtSceneDesc* scene, const IdkPtSkyDesc
             std::vector<uint8_t> c2(n);
             std::vector<uint32_t> k2(n);
             parallel_for(n, T, [&](size_t b, size_t e, int tid) {
+                uint64_t lS = 0, lT = 0, lI = 0, lH = 0;
                 for (size_t gid = b; gid < e; gid++) {
                     Rng rng; rng.seed = (uint32_t)gid * 4096u + st.accumulatedSamples;
                     uint32_t rayIndex = alive[gid];
@@ -1244,8 +1247,9 @@ ORACLE_API int oracle_path_trace(const IdkPtSceneDesc* scene, const IdkPtSkyDesc
                     bool c = ShadeTraceRay(s, st, rng, r, a, false, (uint32_t)gid, 0u, key, rs);
                     rays[rayIndex] = r; aovs[rayIndex] = a;
                     c2[gid] = c ? 1 : 0; k2[gid] = key & (~0u >> (32 - 21));
-                    accS[tid] += rs.steps; accT[tid] += rs.tris; accI[tid] += rs.instances; accH[tid] += rs.hitGeometry ? 1 : 0;
+                    lS += rs.steps; lT += rs.tris; lI += rs.instances; lH += rs.hitGeometry ? 1 : 0;
                 }
+                accS[tid] += lS; accT[tid] += lT; accI[tid] += lI; accH[tid] += lH;
             });
             aliveNext.clear(); keysNext.clear();
             for (size_t gid = 0; gid < n; gid++) if (c2[gid]) { aliveNext.push_back(alive[gid]); keysNext.push_back(k2[gid]); }

@@ -12,6 +12,10 @@ for s in $steps; do
     sweep) timeout 900 python scripts/variant_probe.py --run --eighth --sweep > gpurun_out/variant_probe.log 2>&1; cut -c1-900 gpurun_out/variant_probe.log;;
     bench) timeout 900 python bench.py > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -3 gpurun_out/bench.err; cat gpurun_out/bench.json;;
     benchN) N=$(nvidia-smi -L | wc -l); timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N > gpurun_out/bench_n$N.json 2> gpurun_out/bench_n$N.err; tail -5 gpurun_out/bench_n$N.err; cat gpurun_out/bench_n$N.json;;
+    config4N) N=$(nvidia-smi -L | wc -l); timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $N --workload config4 --steps 10 > gpurun_out/config4_n$N.json 2> gpurun_out/config4_n$N.err; tail -3 gpurun_out/config4_n$N.err; cut -c1-600 gpurun_out/config4_n$N.json;;
+    config4) timeout 900 python bench.py --workload config4 --steps 10 --no-cpu-baseline --no-vxgi > gpurun_out/config4_n1.json 2> gpurun_out/config4_n1.err; tail -3 gpurun_out/config4_n1.err; cut -c1-400 gpurun_out/config4_n1.json;;
+    config3) timeout 900 python bench.py --workload config3 --steps 10 --no-cpu-baseline --no-vxgi > gpurun_out/config3_n1.json 2> gpurun_out/config3_n1.err; tail -3 gpurun_out/config3_n1.err; cut -c1-400 gpurun_out/config3_n1.json;;
+    vxgiN) N=$(nvidia-smi -L | wc -l); timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 scripts/check_vxgi_multigpu.py > gpurun_out/vxgi_n$N.json 2> gpurun_out/vxgi_n$N.err; tail -3 gpurun_out/vxgi_n$N.err; cat gpurun_out/vxgi_n$N.json;;
     ref) timeout 900 python bench.py --impl reference --steps 5 --warmup 1 > gpurun_out/bench_ref.json 2> gpurun_out/bench_ref.err; tail -2 gpurun_out/bench_ref.err; cat gpurun_out/bench_ref.json;;
     ncu) # launch list of the bench command (shares of the step) + --set full captures of the dominant kernels (never a bench number)
        timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches_r02.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-parity --no-vxgi > gpurun_out/bench_under_ncu.log 2>&1

@@ -188,3 +188,44 @@ def test_gpu_voxelize_textured_matches_oracle():
         bad.materials["EmissiveTexture"][0] = 77
         with pytest.raises(vxgi.IdkVxError, match="texture"):
             vx.SetScene(bad)
+
+
+@pytest.mark.gpu
+def test_gpu_vxgi_slabs_and_row_tiles_equal_single_pass():
+    """The multi-GPU decomposition on one device: two contexts voxelise the two z-slabs, the second slab is copied
+    into the first context's grid exactly where the all-gather would put it, the mip chain is built there -- every level equals
+    the single-pass grid (and the oracle's); cone-tracing the image in two row tiles equals the single call."""
+    import torch
+    from idkengine_b200 import multigpu
+    scene, cam = lit_cornell()
+    size = (40, 56, 30)
+    ci = vxgi.create_info(size, GRID_MIN, GRID_MAX)
+    levels, raw, frags = ol.vx_voxelize(scene, ci)
+    w, h = 96, 64
+    frame = scenes.camera_frame(cam, w, h)
+    depth, nrg, mr = ol.synth_gbuffer(scene, frame, w, h)
+    with vxgi.Voxelizer(size, GRID_MIN, GRID_MAX) as a, vxgi.Voxelizer(size, GRID_MIN, GRID_MAX) as b:
+        a.SetScene(scene); b.SetScene(scene)
+        d = size[2]
+        za, zb = multigpu.slab_range(d, 0, 2), multigpu.slab_range(d, 1, 2)
+        assert za == (0, 15) and zb == (15, 30) and multigpu.slab_range(31, 2, 4) == (16, 24)
+        a.SetSlab(*za); b.SetSlab(*zb)
+        sa, sb = a.Render(), b.Render()
+        assert sa.Fragments + sb.Fragments == frags                    # every fragment lands in exactly one slab
+        pa, _ = a.LevelDevicePtr(0)
+        pb, nbytes = b.LevelDevicePtr(0)
+        ta = torch.as_tensor(multigpu.DeviceArray(pa, (d, size[1] * size[0] * 2), "<u4"), device="cuda")
+        tb = torch.as_tensor(multigpu.DeviceArray(pb, (d, size[1] * size[0] * 2), "<u4"), device="cuda")
+        assert not ta[zb[0]:].any() and not tb[:zb[0]].any()            # nothing written outside the own slab
+        ta[zb[0]:zb[1]].copy_(tb[zb[0]:zb[1]])                          # = the all-gather
+        torch.cuda.synchronize()
+        a.Mipmap()
+        for l, lv in enumerate(levels):
+            assert np.array_equal(a.ReadLevel(l).view(np.uint16), lv.view(np.uint16)), f"level {l}"
+        a.SetSlab(0, d)
+        full, cs = a.ConeTrace(frame, depth, nrg, mr)
+        top, c0 = a.ConeTraceRows(frame, depth[:24], nrg[:24], mr[:24], h, 0)
+        bot, c1 = a.ConeTraceRows(frame, depth[24:], nrg[24:], mr[24:], h, 24)
+        assert np.array_equal(np.concatenate([top, bot]), full) and c0.ConeSteps + c1.ConeSteps == cs.ConeSteps
+        with pytest.raises(vxgi.IdkVxError):
+            a.SetSlab(5, 5)
