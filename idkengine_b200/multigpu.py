@@ -86,7 +86,7 @@ def voxelize_multi_gpu(vx, rank, world, device, group=None):
     vx.SetSlab(z0, z1)
     st = vx.Render()
     ptr, nbytes = vx.LevelDevicePtr(0)
-    level0 = torch.as_tensor(DeviceArray(ptr, (d, h * w * 2), "<u4"), device=device)     # 8 bytes per texel as 2 x uint32
+    level0 = torch.as_tensor(DeviceArray(ptr, (d, h * w * 2), "<i4"), device=device)     # 8 bytes per texel as 2 x int32 (NCCL / torch ops have no uint32)
     if world > 1:
         if d % world == 0:
             dist.all_gather_into_tensor(level0.view(-1), level0[z0:z1].reshape(-1), group=group)

@@ -30,7 +30,6 @@ with PathTracer(64, 64, device=local) as pt:
 scene.add_light((-4.5, 5.7, -2.0), (429.8974, 22.459948, 28.425867), 0.3)
 scene.add_light((-0.5, 5.7, -2.0), (8.773416, 506.7525, 28.425867), 0.3)
 scene.add_light((4.5, 5.7, -2.0), (8.773416, 22.459948, 533.77466), 0.3)
-rows = multigpu.tile_rows(h, 8, rank, world)
 with vxgi.Voxelizer(size, device=local) as vx:
     vx.SetScene(scene)
     multigpu.voxelize_multi_gpu(vx, rank, world, dev)          # warm-up (allocations, NCCL channels)
@@ -40,19 +39,16 @@ with vxgi.Voxelizer(size, device=local) as vx:
     st, mst = multigpu.voxelize_multi_gpu(vx, rank, world, dev)
     e1.record(); e1.synchronize()
     total_ms = e0.elapsed_time(e1)
-    # screen-tiled cone trace: the rank's stripes, one call per contiguous run of rows
-    out = np.zeros((len(rows), w, 4), np.float32)
-    cone_ms, steps, i = 0.0, 0, 0
-    while i < len(rows):
-        j = i
-        while j + 1 < len(rows) and rows[j + 1] == rows[j] + 1:
-            j += 1
-        r0, r1 = rows[i], rows[j] + 1
-        o, cs = vx.ConeTraceRows(frame, depth[r0:r1], nrg[r0:r1], mr[r0:r1], h, int(r0))
-        out[i:j + 1] = o
-        cone_ms += cs.ConeTraceMs; steps += cs.ConeSteps
-        i = j + 1
-    gathered = multigpu.all_gather_tiles(torch.as_tensor(out, device=dev), h, 8, world).cpu().numpy() if world > 1 else out
+    # screen-tiled cone trace: ONE contiguous band of rows per rank (8-row stripes would be 68 tail-bound launches of 240 CTAs)
+    r0, r1 = multigpu.slab_range(h, rank, world)
+    out, cs = vx.ConeTraceRows(frame, depth[r0:r1], nrg[r0:r1], mr[r0:r1], h, int(r0))
+    cone_ms, steps = cs.ConeTraceMs, cs.ConeSteps
+    if world > 1:
+        bands = [torch.empty((slab_range[1] - slab_range[0], w, 4), dtype=torch.float32, device=dev) for slab_range in (multigpu.slab_range(h, r, world) for r in range(world))]
+        dist.all_gather(bands, torch.as_tensor(out, device=dev))
+        gathered = torch.cat(bands).cpu().numpy()
+    else:
+        gathered = out
     levels = [vx.ReadLevel(l) for l in range(len(vx.sizes))]
     ok = True
     if rank == 0:

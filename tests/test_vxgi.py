@@ -214,8 +214,8 @@ def test_gpu_vxgi_slabs_and_row_tiles_equal_single_pass():
         assert sa.Fragments + sb.Fragments == frags                    # every fragment lands in exactly one slab
         pa, _ = a.LevelDevicePtr(0)
         pb, nbytes = b.LevelDevicePtr(0)
-        ta = torch.as_tensor(multigpu.DeviceArray(pa, (d, size[1] * size[0] * 2), "<u4"), device="cuda")
-        tb = torch.as_tensor(multigpu.DeviceArray(pb, (d, size[1] * size[0] * 2), "<u4"), device="cuda")
+        ta = torch.as_tensor(multigpu.DeviceArray(pa, (d, size[1] * size[0] * 2), "<i4"), device="cuda")
+        tb = torch.as_tensor(multigpu.DeviceArray(pb, (d, size[1] * size[0] * 2), "<i4"), device="cuda")
         assert not ta[zb[0]:].any() and not tb[:zb[0]].any()            # nothing written outside the own slab
         ta[zb[0]:zb[1]].copy_(tb[zb[0]:zb[1]])                          # = the all-gather
         torch.cuda.synchronize()
