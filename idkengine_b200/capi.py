@@ -94,7 +94,7 @@ EXPORTS = [
     "idkpt_result_device_ptr", "idkpt_tile_rows",
     "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_trace_rays_any", "idkpt_shadows_ray_traced",
     "idkpt_set_skinning_data", "idkpt_skin_vertices", "idkpt_blas_refit", "idkpt_read_range", "idkpt_post_process", "idkpt_ldr_device_ptr", "idkpt_abi_version",
-    "idkpt_denoise", "idkpt_denoise_device_ptrs", "idkpt_denoise_import_output",
+    "idkpt_denoise", "idkpt_denoise_device_ptrs", "idkpt_denoise_import_output", "idkpt_tlas_build",
 ]
 
 
@@ -286,6 +286,8 @@ def load(path=None):
     L.idkpt_set_textures.argtypes = [c_vp, c_vp, c_u64]
     L.idkpt_sync.restype = c_i32
     L.idkpt_sync.argtypes = [c_vp]
+    L.idkpt_tlas_build.restype = c_i32
+    L.idkpt_tlas_build.argtypes = [c_vp, c_i32, P(c_f)]
     L.idkpt_denoise.restype = c_i32
     L.idkpt_denoise.argtypes = [c_vp, P(IdkPtDenoiseSettings), P(c_f)]
     L.idkpt_denoise_device_ptrs.restype = c_i32

@@ -78,7 +78,7 @@ struct IdkPtCtx {
     bool haveDenoised = false;
 
     // dynamic geometry: unskinned vertices, joint matrices, refit scratch (parents + locks of the largest BLAS)
-    DevBuf unskinned, joints, refitParents, refitLocks;
+    DevBuf unskinned, joints, refitParents, refitLocks, tlasScratch;
     uint64_t unskinnedCount = 0;
     std::vector<uint32_t> unskinnedMaxJoint;   // per vertex max(JointIndices), host copy for range validation
     std::vector<GpuBlasDesc> hostDescs;
@@ -549,7 +549,7 @@ IDKPT_API void idkpt_destroy(IdkPtCtx* ctx) {
                      &ctx->images[0], &ctx->images[1], &ctx->images[2], &ctx->counters, &ctx->countLog, &ctx->skyFaces,
                      &ctx->texPixels, &ctx->texRecs, &ctx->srgbLut, &ctx->bloomDown, &ctx->bloomUp, &ctx->postConsts, &ctx->ldr,
                      &ctx->unskinned, &ctx->joints, &ctx->refitParents, &ctx->refitLocks, &ctx->scratch[0], &ctx->scratch[1], &ctx->scratch[2],
-                     &ctx->oidn[0], &ctx->oidn[1], &ctx->oidn[2], &ctx->oidn[3], &ctx->denoiseWork[0], &ctx->denoiseWork[1], &ctx->denoised};
+                     &ctx->tlasScratch, &ctx->oidn[0], &ctx->oidn[1], &ctx->oidn[2], &ctx->oidn[3], &ctx->denoiseWork[0], &ctx->denoiseWork[1], &ctx->denoised};
     for (DevBuf* b : all) release(*b);
     for (int i = 0; i < IDK_MAX_LANES; i++) release_lane(ctx->lanes[i], false);
     for (cudaEvent_t ev : ctx->events) cudaEventDestroy(ev);
@@ -1667,6 +1667,41 @@ IDKPT_API int idkpt_blas_refit(IdkPtCtx* ctx, uint32_t first, uint32_t count, fl
     if (e == cudaSuccess && kernelMs) cudaEventElapsedTime(kernelMs, e0, e1);
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_blas_refit: ") + cudaGetErrorString(e); return IDKPT_ERR_CUDA; }
+    ctx->accumulatedSamples = 0;
+    return IDKPT_OK;
+}
+
+// BVH.TlasBuild on the device (BVH.cs:278-298, TLAS.cs:28-141): see k_tlas_build.
+IDKPT_API int idkpt_tlas_build(IdkPtCtx* ctx, int32_t searchRadius, float* kernelMs) {
+    if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
+    DRAIN_PENDING("idkpt_tlas_build");
+    if (kernelMs) *kernelMs = 0.0f;
+    if (!ctx->haveScene) return fail(ctx, IDKPT_ERR_NO_SCENE, "idkpt_tlas_build: no scene");
+    if (!ctx->counts.UseTlas) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_tlas_build: the scene was set without UseTlas (no TLAS node array to fill)");
+    if (searchRadius < 1 || searchRadius > 1024) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_tlas_build: search radius out of range (TLAS.BuildSettings.SearchRadius, default 15)");
+    const uint64_t n = ctx->counts.BlasInstanceCount;
+    if (n > 65536) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_tlas_build: more than 65536 instances (single-CTA build); build on the host and idkpt_update_range");
+    if (ctx->treeletNodes) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_tlas_build: not available with the treelet node layout (IDKPT_TREELET_PAIRS)");
+    CK(cudaSetDevice(ctx->device));
+    const size_t nodeCount = 2 * n - 1;
+    const size_t tempOff = 0, leavesOff = nodeCount * 32, keysOff = leavesOff + n * 32, prefOff = keysOff + n * 4;
+    CK(ensure(ctx->tlasScratch, prefOff + n * 4 + 64));
+    TlasBuildArgs a;
+    a.blasNodes = (const float4*)ctx->nodes.p; a.descs = (const GpuBlasDesc*)ctx->descs.p; a.instances = (const GpuBlasInstance*)ctx->instances.p;
+    a.xforms = (const float4*)ctx->xforms.p; a.nodes = (float4*)ctx->tlas.p;
+    a.temp = (float4*)((char*)ctx->tlasScratch.p + tempOff); a.leaves = (float4*)((char*)ctx->tlasScratch.p + leavesOff);
+    a.keys = (uint32_t*)((char*)ctx->tlasScratch.p + keysOff); a.pref = (int*)((char*)ctx->tlasScratch.p + prefOff);
+    a.n = (int)n; a.searchRadius = searchRadius;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    cudaEventRecord(e0, ctx->stream);
+    k_tlas_build<<<1, 1024, 0, ctx->stream>>>(a);
+    cudaEventRecord(e1, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    if (e == cudaSuccess && kernelMs) cudaEventElapsedTime(kernelMs, e0, e1);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_tlas_build: ") + cudaGetErrorString(e); return IDKPT_ERR_CUDA; }
     ctx->accumulatedSamples = 0;
     return IDKPT_OK;
 }

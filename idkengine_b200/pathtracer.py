@@ -130,6 +130,12 @@ class PathTracer:
         self._check(self._lib.idkpt_blas_refit(self._ctx, first, count, ctypes.byref(ms)), "idkpt_blas_refit")
         return ms.value
 
+    def TlasBuild(self, search_radius=15):
+        """BVH.TlasBuild on the device (BVH.cs:278-298, TLAS.cs:28-141) from the refitted roots and current transforms. Returns kernel ms."""
+        ms = ctypes.c_float()
+        self._check(self._lib.idkpt_tlas_build(self._ctx, search_radius, ctypes.byref(ms)), "idkpt_tlas_build")
+        return ms.value
+
     def SetTextures(self, textures):
         """Replace the material texture table (list of dict(pixels, srgb, wrap_s, wrap_t), as host.Scene.textures)."""
         arr, keep = capi.texture_descs(textures)

@@ -129,6 +129,7 @@ public:
     // ---- presentation / interop -------------------------------------------------------------------------------------------
     void PresentAsync(void* pinnedHostRgba32f, uint64_t bytes, IdkPtImage which = IDKPT_IMAGE_RESULT) { check(idkpt_present_async(ctx_, which, pinnedHostRgba32f, bytes), "idkpt_present_async"); }
     void PresentWait() { check(idkpt_present_wait(ctx_), "idkpt_present_wait"); }
+    float TlasBuild(int searchRadius = 15) { float ms = 0.0f; check(idkpt_tlas_build(ctx_, searchRadius, &ms), "idkpt_tlas_build"); return ms; }   // BVH.TlasBuild on the device
     float Denoise(const IdkPtDenoiseSettings& s) { float ms = 0.0f; check(idkpt_denoise(ctx_, &s, &ms), "idkpt_denoise"); return ms; }   // PathTracerPipeline.Denoise
     std::vector<float> Denoised() const { return read(IDKPT_IMAGE_DENOISED); }
     void RegisterHostBuffer(void* hostPtr, uint64_t bytes) { check(idkpt_register_host_buffer(ctx_, hostPtr, bytes), "idkpt_register_host_buffer"); }

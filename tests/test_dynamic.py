@@ -142,3 +142,41 @@ def test_skin_refit_tlas_bit_exact():
     o = ol.path_trace(expect, frame, s, w, h, sky=(0.6, 0.7, 0.9), accumulated=o.accumulated, result=res)
     assert np.array_equal(moved.view(np.uint32), res.view(np.uint32))
     assert not np.array_equal(moved, still)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid,radius", [(3, 15), (2, 2), (4, 7)])
+def test_device_tlas_build_equals_host_build(grid, radius):
+    """idkpt_tlas_build (BVH.TlasBuild + TLAS.Build PLOC on the device, no read-back) == the host mirror's TLAS.Build on the same
+    roots and transforms, node for node, including after instances moved (transform update) -- then rendering through it."""
+    from idkengine_b200.pathtracer import PathTracer
+    scene, cam = scenes.instance_grid(grid, threads=1)
+    scene.build_tlas(search_radius=radius)
+    want = scene.tlas_nodes.copy()
+    n = len(scene.blas_instances)
+    w, h = 96, 64
+    s = capi.default_settings()
+    s.RayDepth = 4
+    frame = scenes.camera_frame(cam, w, h)
+    with PathTracer(w, h, s) as pt:
+        pt.SetScene(scene); pt.SetSky((0.6, 0.7, 0.9)); pt.SetFrame(frame)
+        ms = pt.TlasBuild(radius)
+        got = pt.ReadRange(capi.IDKPT_ARRAY_TLAS_NODES, 0, 2 * n - 1)
+        assert ms > 0 and got.tobytes() == want.tobytes()
+        # move a third of the instances, rebuild on both sides
+        moved = scene.mesh_transforms.copy()
+        for k in range(0, len(moved), 3):
+            moved["ModelMatrix"][k][:, 3] += np.array([0.7, 0.15 * (k % 4), -0.5], np.float32)
+            m = np.eye(4); m[:3, :] = moved["ModelMatrix"][k]
+            moved["InvModelMatrix"][k] = np.linalg.inv(m)[:3, :].astype(np.float32)
+        pt.UpdateRange(capi.IDKPT_ARRAY_MESH_TRANSFORMS, 0, moved)
+        pt.TlasBuild(radius)
+        scene.mesh_transforms = moved
+        scene.build_tlas(search_radius=radius)
+        got2 = pt.ReadRange(capi.IDKPT_ARRAY_TLAS_NODES, 0, 2 * n - 1)
+        assert got2.tobytes() == scene.tlas_nodes.tobytes() and got2.tobytes() != want.tobytes()
+        pt.Compute()
+        img = pt.Result
+    res = np.zeros((h, w, 4), np.float32)
+    ol.path_trace(scene, frame, s, w, h, sky=(0.6, 0.7, 0.9), result=res)
+    assert np.array_equal(img.view(np.uint32), res.view(np.uint32))
