@@ -1680,7 +1680,7 @@ IDKPT_API int idkpt_tlas_build(IdkPtCtx* ctx, int32_t searchRadius, float* kerne
     if (!ctx->counts.UseTlas) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_tlas_build: the scene was set without UseTlas (no TLAS node array to fill)");
     if (searchRadius < 1 || searchRadius > 1024) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_tlas_build: search radius out of range (TLAS.BuildSettings.SearchRadius, default 15)");
     const uint64_t n = ctx->counts.BlasInstanceCount;
-    if (n > 65536) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_tlas_build: more than 65536 instances (single-CTA build); build on the host and idkpt_update_range");
+    if (n > 16384) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_tlas_build: more than 16384 instances (single-CTA build); build on the host and idkpt_update_range");
     if (ctx->treeletNodes) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_tlas_build: not available with the treelet node layout (IDKPT_TREELET_PAIRS)");
     CK(cudaSetDevice(ctx->device));
     const size_t nodeCount = 2 * n - 1;

@@ -263,6 +263,54 @@ def test_two_rank_gloo_tile_gather(tmp_path):
     assert "GLOO_OK" in out.stdout
 
 
+def test_slab_partition_properties():
+    """multigpu.slab_range (z-slabs of the voxel grid / row bands of the cone trace): a partition of [0, n) into `world`
+    contiguous ranges whose sizes differ by at most one, equal when world divides n (the in-place all-gather case)."""
+    for n in (1, 7, 30, 31, 384, 1080):
+        for world in (1, 2, 3, 4, 8):
+            rs = [multigpu.slab_range(n, r, world) for r in range(world)]
+            assert rs[0][0] == 0 and rs[-1][1] == n
+            assert all(rs[i][1] == rs[i + 1][0] for i in range(world - 1))
+            sizes = [b - a for a, b in rs]
+            assert max(sizes) - min(sizes) <= 1 and (n % world != 0 or len(set(sizes)) == 1)
+
+
+GLOO_SLAB_WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1]); sys.path.insert(0, os.path.join(sys.argv[1], "tests"))
+import numpy as np, torch, torch.distributed as dist
+import oracle_lib as ol
+from idkengine_b200 import scenes, vxgi, multigpu
+dist.init_process_group("gloo")
+rank, world = dist.get_rank(), dist.get_world_size()
+scene, cam = scenes.cornell_1k(threads=1)
+scene.add_light((0.0, 1.6, 0.3), (6.0, 5.5, 5.0), 0.2)
+ci = vxgi.create_info((20, 24, 18), (-1.2, -0.2, -1.2), (1.2, 2.2, 1.2))
+levels, raw, frags = ol.vx_voxelize(scene, ci)
+level0 = levels[0].view(np.uint16).reshape(18, -1).astype(np.int32)       # [z, y*x*4]
+z0, z1 = multigpu.slab_range(18, rank, world)
+mine = np.zeros_like(level0); mine[z0:z1] = level0[z0:z1]                 # what this rank's slab voxelisation leaves in its grid
+parts = [torch.zeros((multigpu.slab_range(18, r, world)[1] - multigpu.slab_range(18, r, world)[0], level0.shape[1]), dtype=torch.int32) for r in range(world)]
+dist.all_gather(parts, torch.from_numpy(mine[z0:z1].copy()))
+merged = torch.cat(parts).numpy()
+assert np.array_equal(merged, level0), "slab gather differs from the full grid"
+if rank == 0: print("GLOO_SLAB_OK")
+'''
+
+
+def test_two_rank_gloo_slab_gather(tmp_path):
+    """Host logic of the multi-GPU VXGI split on CPU (gloo, world_size 2): contiguous z-slabs of the oracle's level 0, gathered in
+    rank order, are the full level."""
+    script = tmp_path / "slab_worker.py"
+    script.write_text(GLOO_SLAB_WORKER)
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", MASTER_PORT="29537")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29537", str(script), REPO],
+                         capture_output=True, text=True, env=env, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "GLOO_SLAB_OK" in out.stdout
+
+
 def test_oracle_any_hit_and_shadows(multi_blas):
     """Oracle-only sanity for the 8f.1 rows: any-hit occlusion == closest-hit "found something"; the shadow pass is dark
     behind occluders, lit in the open, and leaves sky pixels untouched."""
