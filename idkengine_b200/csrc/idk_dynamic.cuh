@@ -153,6 +153,7 @@ struct TlasBuildArgs {
     float4* leaves;                  // scratch: n nodes
     uint32_t* keys;                  // scratch: n
     int* pref;                       // scratch: n
+    int* need;                       // scratch: 2n-1; need[0] on exit = traversal stack entries the TLAS walk needs (tree height)
     int n, searchRadius;
 };
 
@@ -289,5 +290,14 @@ __global__ void __launch_bounds__(1024) k_tlas_build(TlasBuildArgs a) {
             for (int i = newBegin + tid; i < end; i += nt) { a.nodes[2 * i] = a.temp[2 * i]; a.nodes[2 * i + 1] = a.temp[2 * i + 1]; }
         }
         __syncthreads();
+    }
+    // stack entries the TLAS walk (BVHIntersect.glsl:205-272, fixed 24-entry stack) needs = the height of the tree; children
+    // always follow their parent in the array, so one backward sweep suffices. The host rejects a TLAS that is too deep.
+    if (tid == 0) {
+        for (int i = nodeCount - 1; i >= 0; i--) {
+            const uint32_t w = __float_as_uint(a.nodes[2 * i].w);
+            const int c = (int)(w & 0x7FFFFFFFu);
+            a.need[i] = (w >> 31) ? 0 : 1 + max(a.need[c], a.need[c + 1]);
+        }
     }
 }

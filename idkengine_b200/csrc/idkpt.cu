@@ -457,6 +457,16 @@ static const char* validate_blas(const GpuBlasNode* nodes, const GpuBlasDesc& d,
     return nullptr;
 }
 
+// Height of a host-provided TLAS (= stack entries the walk needs); children follow their parent (validated before).
+static int tlas_height(const GpuTlasNode* t, uint64_t count) {
+    std::vector<int> need(count, 0);
+    for (int64_t i = (int64_t)count - 1; i >= 0; i--) {
+        const uint32_t w = t[i].IsLeafAndChildOrInstanceId, c = w & 0x7FFFFFFFu;
+        need[i] = (w >> 31) ? 0 : 1 + std::max(need[c], need[c + 1]);
+    }
+    return count ? need[0] : 0;
+}
+
 static void gather_teardown(IdkPtCtx* ctx) {
     for (int b = 0; b < 2; b++)
         for (int p = 0; p < IDK_MAX_PEERS; p++) {
@@ -579,6 +589,8 @@ IDKPT_API int idkpt_set_scene(IdkPtCtx* ctx, const IdkPtSceneDesc* s) {
             if ((w >> 31) ? (id >= s->BlasInstanceCount) : (id <= i || (uint64_t)id + 1 >= s->TlasNodeCount))
                 return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: malformed TLAS node (child / instance id out of range)");
         }
+        if (tlas_height(s->TlasNodes, s->TlasNodeCount) > IDK_TLAS_STACK_SIZE)
+            return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_set_scene: TLAS deeper than the 24-entry traversal stack of the TLAS walk (BVHIntersect.glsl:4)");
     }
     if (s->BlasTriangleCount >= (1ull << 31) || s->BlasNodeCount >= (1ull << 31)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_set_scene: scene too large");
     // validate indices the kernels will chase (a bad host array must not become a device fault)
@@ -759,6 +771,8 @@ IDKPT_API int idkpt_update_range(IdkPtCtx* ctx, IdkPtArrayId which, uint64_t fir
             if ((w >> 31) ? (id >= ctx->counts.BlasInstanceCount) : (id <= first + i || (uint64_t)id + 1 >= ctx->counts.TlasNodeCount))
                 return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_update_range: malformed TLAS node (child / instance id out of range)");
         }
+        if (first == 0 && count == ctx->counts.TlasNodeCount && tlas_height(t, count) > IDK_TLAS_STACK_SIZE)
+            return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_update_range: TLAS deeper than the 24-entry traversal stack of the TLAS walk (BVHIntersect.glsl:4)");
     }
     if (which == IDKPT_ARRAY_MATERIALS) {
         const GpuMaterial* m = (const GpuMaterial*)data;
@@ -1684,13 +1698,14 @@ IDKPT_API int idkpt_tlas_build(IdkPtCtx* ctx, int32_t searchRadius, float* kerne
     if (ctx->treeletNodes) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_tlas_build: not available with the treelet node layout (IDKPT_TREELET_PAIRS)");
     CK(cudaSetDevice(ctx->device));
     const size_t nodeCount = 2 * n - 1;
-    const size_t tempOff = 0, leavesOff = nodeCount * 32, keysOff = leavesOff + n * 32, prefOff = keysOff + n * 4;
-    CK(ensure(ctx->tlasScratch, prefOff + n * 4 + 64));
+    const size_t tempOff = 0, leavesOff = nodeCount * 32, keysOff = leavesOff + n * 32, prefOff = keysOff + n * 4, needOff = prefOff + n * 4;
+    CK(ensure(ctx->tlasScratch, needOff + nodeCount * 4 + 64));
     TlasBuildArgs a;
     a.blasNodes = (const float4*)ctx->nodes.p; a.descs = (const GpuBlasDesc*)ctx->descs.p; a.instances = (const GpuBlasInstance*)ctx->instances.p;
     a.xforms = (const float4*)ctx->xforms.p; a.nodes = (float4*)ctx->tlas.p;
     a.temp = (float4*)((char*)ctx->tlasScratch.p + tempOff); a.leaves = (float4*)((char*)ctx->tlasScratch.p + leavesOff);
     a.keys = (uint32_t*)((char*)ctx->tlasScratch.p + keysOff); a.pref = (int*)((char*)ctx->tlasScratch.p + prefOff);
+    a.need = (int*)((char*)ctx->tlasScratch.p + needOff);
     a.n = (int)n; a.searchRadius = searchRadius;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
@@ -1703,6 +1718,12 @@ IDKPT_API int idkpt_tlas_build(IdkPtCtx* ctx, int32_t searchRadius, float* kerne
     cudaEventDestroy(e0); cudaEventDestroy(e1);
     if (e != cudaSuccess) { ctx->lastError = std::string("idkpt_tlas_build: ") + cudaGetErrorString(e); return IDKPT_ERR_CUDA; }
     ctx->accumulatedSamples = 0;
+    int need = 0;
+    CK(cudaMemcpy(&need, a.need, 4, cudaMemcpyDeviceToHost));
+    if (need > IDK_TLAS_STACK_SIZE) {     // the walk's stack is fixed (BVHIntersect.glsl:4): refuse to trace through a TLAS it cannot hold
+        ctx->haveScene = false;
+        return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_tlas_build: the built TLAS is deeper than the 24-entry traversal stack of the TLAS walk (scene invalidated; set it again)");
+    }
     return IDKPT_OK;
 }
 

@@ -195,6 +195,31 @@ def test_tlas_walk_in_the_production_kernel():
         assert feq(pt.Result, o["result"])
 
 
+def test_tlas_deeper_than_the_walk_stack_is_rejected():
+    """The TLAS walk has a fixed 24-entry stack (BVHIntersect.glsl:4). A host TLAS that needs more (here a 27-deep chain over 28
+    instances) is an error at hand-over, not a device fault later."""
+    from idkengine_b200 import gpu_types as gt
+    scene, cam = scenes.instance_grid(3, threads=1)
+    n = len(scene.blas_instances)
+    good = scene.tlas_nodes
+    chain = np.zeros(2 * n - 1, gt.GpuTlasNode)
+    lo, hi = good["Min"][0], good["Max"][0]
+    for k in range(n - 1):                      # node 2k: internal with children (2k+1 = leaf k, 2k+2 = rest of the chain)
+        chain["Min"][2 * k], chain["Max"][2 * k] = lo, hi
+        chain["IsLeafAndChildOrInstanceId"][2 * k] = 2 * k + 1
+        chain["Min"][2 * k + 1], chain["Max"][2 * k + 1] = lo, hi
+        chain["IsLeafAndChildOrInstanceId"][2 * k + 1] = 0x80000000 | k
+    chain["Min"][2 * n - 2], chain["Max"][2 * n - 2] = lo, hi
+    chain["IsLeafAndChildOrInstanceId"][2 * n - 2] = 0x80000000 | (n - 1)
+    with PathTracer(32, 32) as pt:
+        pt.SetScene(scene)                       # the PLOC tree is fine
+        with pytest.raises(IdkPtError, match="deeper"):
+            pt.UpdateRange(capi.IDKPT_ARRAY_TLAS_NODES, 0, chain)
+        scene.tlas_nodes = chain
+        with pytest.raises(IdkPtError, match="deeper"):
+            pt.SetScene(scene)
+
+
 def test_compaction_epoch_wraps_without_hanging(cornell):
     """The decoupled look-back's status words carry a 30-bit epoch; a long-running renderer wraps it (advisor finding,
     round 1: the kernel used to spin forever). IDKPT_DEBUG_EPOCH_START puts a fresh context 6 compactions before the wrap."""
