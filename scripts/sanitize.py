@@ -68,7 +68,9 @@ with PathTracer(80, 56, lanes=3) as pt:
     for _ in range(3):
         pt.ComputeAsync()
     pt.Sync()
-print("tlas phase + cube sky ok")
+    pt.TlasBuild(15); pt.TlasBuild(2)
+    pt.Compute()
+print("tlas phase + cube sky + device tlas build ok")
 comp = copy.copy(scene)
 comp.textures = []
 rng = np.random.default_rng(4)
@@ -94,7 +96,10 @@ with PathTracer(w, h, s2) as pt:
     shadowed.lights = comp.lights.copy(); shadowed.lights["PointShadowIndex"][:] = 0
     with vxgi.Voxelizer((20, 16, 24), (-3.1, -0.1, -3.1), (3.1, 4.1, 3.1)) as vx:
         vx.SetScene(shadowed); vx.SetShadowTracer(pt); vx.Render()
-print("bcn + denoise + point shadows ok")
+        vx.SetSlab(5, 17); vx.Render(); vx.LevelDevicePtr(0); vx.Mipmap(); vx.SetSlab(0, 24)
+        f3 = scenes.camera_frame(cam, 40, 24)
+        vx.ConeTraceRows(f3, np.full((8, 40), 0.95, np.float32), np.full((8, 40, 2), 0.5, np.float32), np.full((8, 40, 2), 0.5, np.float32), 24, 8)
+print("bcn + denoise + point shadows + slabs ok")
 
 with vxgi.Voxelizer((24, 20, 28), (-3.1, -0.1, -3.1), (3.1, 4.1, 3.1)) as vx:
     vx.SetScene(scene)
