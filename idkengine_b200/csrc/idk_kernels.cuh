@@ -355,7 +355,7 @@ __global__ void __launch_bounds__(IDK_BLOCK) k_traverse(TraverseArgs a) {
 //   LEAF   lanes with a pending range test ONE triangle.
 // Each iteration the warp votes (ballots) which phase to run: a phase runs when enough lanes wait for it or nothing
 // else can run. Traversal stacks live in shared memory, one column per thread (the reference's layout).
-struct TraverseTuning { int setupThreshold; int leafThreshold; int packRays; int setupThresholdStaged; };   // packRays: 32 rays per warp whatever the count (throughput mode: several samples share the SMs)
+struct TraverseTuning { int setupThreshold; int leafThreshold; int packRays; int setupThresholdStaged; int packCta; };   // packRays: 32 rays per warp whatever the count (throughput mode: several samples share the SMs)
 
 // TMA (bulk async copy) staging of the hot top of the BVH into shared memory: one elected thread arms an mbarrier with
 // the byte count and issues cp.async.bulk global -> shared; every thread then waits on the barrier phase.
@@ -425,6 +425,10 @@ __global__ void __launch_bounds__(IDK_T2_BLOCK) k_traverse2(TraverseArgs a, Trav
     // Latency regime (few rays, e.g. late bounces or a 1/8 screen tile): spread the rays over ALL resident warps instead
     // of packing 32 per warp -- a warp that carries few rays has short BOX/LEAF/SETUP rounds and little L1 wavefront
     // serialisation, so the longest ray (which bounds the launch) finishes sooner. quota = rays per warp, 32 in the bulk.
+    // Pipelined launches (packRays): a launch with few rays needs few CTAs. Only the first ceil(count / (block * packRays)) CTAs take
+    // part, the others retire at once and leave their registers / shared memory to the other samples' kernels (a CTA that keeps one
+    // busy warp holds a quarter of an SM). packCta = rays per thread a participating CTA is expected to take (1 = tightest packing, 0 = every CTA takes part).
+    if (tune.packCta > 0 && (uint64_t)blockIdx.x * (IDK_T2_BLOCK * (uint32_t)tune.packCta) >= (uint64_t)count && blockIdx.x > 0) return;
     const uint32_t totalWarps = gridDim.x * (IDK_T2_BLOCK / 32);
     const uint32_t quota = tune.packRays ? 32u : min(32u, max(1u, (count + totalWarps - 1) / totalWarps));
 #if IDK_STAGED_FETCH

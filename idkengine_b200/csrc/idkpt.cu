@@ -103,7 +103,8 @@ struct IdkPtCtx {
     int traverseBlocksLane = 0, traverse1BlocksLane = 0;   // grids of the asynchronous path: the resident-block budget split between the lanes
     int traverseVariant = 3;       // 1 = k_traverse (one ray per lane, reference loop), 2 = k_traverse2 (phase-scheduled warps),
                                    // 3 = k_traverse for the coherent primary rays, k_traverse2 for every bounce (default)
-    TraverseTuning tune = {12, 4, 0, 6};   // swept on B200 (profiles/r01b_tuning.txt); packRays is set per launch
+    TraverseTuning tune = {12, 4, 0, 6, 0};   // swept on B200 (profiles/r01b_tuning.txt); packRays is set per launch
+    int packCta = 0;                 // IDKPT_PACK_CTA: pipelined launches let only ceil(rays / (256 * k)) CTAs take part (0 = all; measured neutral at k = 1, slower at 2 / 4: profiles/r02_traverse_experiments.txt)
     int packAsync = 1;               // IDKPT_PACK_ASYNC: asynchronous (pipelined) launches pack 32 rays per warp instead of spreading few rays over all warps
     size_t stackBytes = 0;
     size_t traverse2Smem = 0;      // treelet + stacks
@@ -533,6 +534,7 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
     if (const char* v = getenv("IDKPT_TUNE_LEAF")) ctx->tune.leafThreshold = std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("IDKPT_TUNE_SETUP_STAGED")) ctx->tune.setupThresholdStaged = std::max(1, std::min(32, atoi(v)));
     if (const char* v = getenv("IDKPT_PACK_ASYNC")) ctx->packAsync = atoi(v) != 0;
+    if (const char* v = getenv("IDKPT_PACK_CTA")) ctx->packCta = std::max(0, atoi(v));
     if (const int fl = (ci->Flags >> 8) & 15) ctx->laneCount = std::min(IDK_MAX_LANES, fl);   // IDKPT_CREATE_LANES(n)
     if (const char* v = getenv("IDKPT_LANES")) ctx->laneCount = std::max(1, std::min(IDK_MAX_LANES, atoi(v)));
     if (const char* v = getenv("IDKPT_DEBUG_EPOCH_START")) ctx->epochStart = (uint32_t)strtoul(v, nullptr, 0) & IDK_EPOCH_MASK;
@@ -1035,6 +1037,7 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                 const int tb = async ? ctx->traverseBlocksLane : ctx->traverseBlocks;
                 TraverseTuning tune = ctx->tune;
                 tune.packRays = (async && ctx->packAsync) ? 1 : 0;
+                tune.packCta = (async && ctx->packAsync) ? ctx->packCta : 0;
                 if (ctx->sc.useTlas) {       // the TLAS walk is a fourth phase of the production kernel (BVHIntersect.glsl:205-272)
                     if (wantStats) k_traverse2<true, false, true><<<ctx->traverseBlocksStats, IDK_T2_BLOCK, ctx->traverse2Smem, ls>>>(ta, tune);
                     else k_traverse2<false, false, true><<<tb, IDK_T2_BLOCK, ctx->traverse2Smem, ls>>>(ta, tune);

@@ -84,8 +84,7 @@ def run(eighth):
     libs = [None] + sorted(os.path.join(VDIR, f) for f in os.listdir(VDIR) if f.endswith(".so")) if os.path.isdir(VDIR) else [None]
     jobs = [(lib, {}) for lib in libs]
     if "--sweep" in sys.argv:      # scheduling thresholds of the default build (IDKPT_TUNE_SETUP / IDKPT_TUNE_LEAF)
-        jobs += [(None, {"IDKPT_PACK_ASYNC": "0"})]
-        jobs += [(lib, {"IDKPT_LANE_BLOCKS_PER_SM": str(v)}) for lib in libs if lib and "t2b" in lib for v in (1, 4)]
+        jobs += [(None, {"IDKPT_PACK_CTA": str(v)}) for v in (0, 2, 4)]
     results = []
     for lib, extra in jobs:
         env = dict(os.environ)
