@@ -297,6 +297,9 @@ __device__ __forceinline__ float4 ldg4(const float4* p) { return __ldg(p); }
 #ifndef IDK_FAST_VOTE
 #define IDK_FAST_VOTE 0      // k_traverse2: one ballot instead of four when (nearly) every lane is in the BOX phase
 #endif
+#ifndef IDK_BOX_LOOP
+#define IDK_BOX_LOOP 0       // k_traverse2: stay in the BOX phase with one ballot per round while >= 33 - min(thresholds) lanes are in it
+#endif
 #ifndef IDK_LEAF_LOOP
 #define IDK_LEAF_LOOP 0      // k_traverse2: a LEAF round tests a lane's whole pending range instead of one triangle
 #endif

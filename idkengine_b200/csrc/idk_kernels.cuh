@@ -745,6 +745,12 @@ __global__ void __launch_bounds__(IDK_T2_BLOCK) k_traverse2(TraverseArgs a, Trav
             }
         } else {
             // ------------------------------------------------------------------ BOX (one sibling pair)
+#if IDK_BOX_LOOP
+            // While (nearly) every lane stays in BOX no other phase can reach its threshold, so the full four-ballot vote would pick
+            // BOX again: stay in this loop with one ballot per round instead (same schedule, fewer instructions).
+            const int boxStay = 33 - min(setupThreshold, leafThreshold);
+            do {
+#endif
             if (state == ST_BOX) {
                 if (STATS) { S++; cost += 1.0f; }
                 float4 lA, lB, rA, rB;
@@ -790,6 +796,9 @@ __global__ void __launch_bounds__(IDK_T2_BLOCK) k_traverse2(TraverseArgs a, Trav
                     IDK_BLAS_DONE();
                 }
             }
+#if IDK_BOX_LOOP
+            } while (__popc(__ballot_sync(0xffffffffu, state == ST_BOX)) >= boxStay);
+#endif
         }
     }
 #undef IDK_STACK_RESET

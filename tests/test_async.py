@@ -137,3 +137,29 @@ def test_async_resize_and_stats_fallback(cornell):
         for _ in range(5):
             pt.Compute()
         assert np.array_equal(got, pt.Result)
+
+
+def test_tiled_present_into_a_registered_host_frame(cornell):
+    """Multi-GPU presentation path on one device: a tiled context delivers ONLY its own stripes, at their final rows, into a
+    full-frame host buffer page-locked through idkpt_register_host_buffer (the strided copy of idkpt_present_async)."""
+    from idkengine_b200.pathtracer import PathTracer
+    scene, cam = cornell
+    w, h = 96, 84                       # 10.5 stripes of 8 rows: the last stripe of the image is partial
+    s = capi.default_settings()
+    frame = scenes.camera_frame(cam, w, h)
+    host = np.full((h, w, 4), -7.0, np.float32)
+    for tile in ((8, 0, 3), (8, 1, 3), (8, 2, 3)):
+        with PathTracer(w, h, s, tile=tile, lanes=2) as pt:
+            pt.SetScene(scene); pt.SetSky((0.6, 0.7, 0.9)); pt.SetFrame(frame)
+            pt.RegisterHostBuffer(host.ctypes.data, host.nbytes)
+            before = host.copy()
+            pt.ComputeAsync(); pt.ComputeAsync()
+            pt.PresentAsync(host.ctypes.data, host.nbytes)
+            pt.PresentWait()
+            rows = pt.TileRows()
+            other = np.setdiff1d(np.arange(h), rows)
+            assert np.array_equal(host[other], before[other])             # nobody else's rows were touched
+            assert np.array_equal(host[rows], pt.Result[rows])
+            assert len(rows) % 8 != 0 or tile[1] != 1                      # tile 1 owns the partial last stripe (rows 80..83)
+            pt.UnregisterHostBuffer(host.ctypes.data)
+    assert (host != -7.0).all()                                            # the three tiles together filled the frame
