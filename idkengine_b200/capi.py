@@ -26,7 +26,7 @@ class IdkPtCreateInfo(ctypes.Structure):
 IDKPT_TEX_RGBA8_UNORM, IDKPT_TEX_RGBA8_SRGB = 0, 1
 IDKPT_TEX_BC7_UNORM, IDKPT_TEX_BC7_SRGB, IDKPT_TEX_BC5_RG_UNORM, IDKPT_TEX_BC4_R_UNORM = 2, 3, 4, 5
 IDKPT_TEX_RG32F, IDKPT_TEX_R32F, IDKPT_TEX_RGBA32F = 6, 7, 8
-IDKPT_TEX_FLAG_R_FROM_B = 1
+IDKPT_TEX_FLAG_R_FROM_B, IDKPT_TEX_FLAG_MAG_NEAREST = 1, 2
 GL_REPEAT, GL_CLAMP_TO_EDGE, GL_MIRRORED_REPEAT = 10497, 33071, 33648
 
 

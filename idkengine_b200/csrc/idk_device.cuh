@@ -89,7 +89,7 @@ struct TexRec {
     int w, h;
     int wrapS, wrapT;             // GL enums: 10497 REPEAT, 33071 CLAMP_TO_EDGE, 33648 MIRRORED_REPEAT
     int srgb;                     // rgb decoded through srgbLut before filtering (GL_SRGB8_ALPHA8 / BC7 sRGB)
-    int kind;                     // bits 0-7: texel storage kind, bit 8: R channel reads B (IDKPT_TEX_FLAG_R_FROM_B)
+    int kind;                     // bits 0-7: texel storage kind, bit 8: R channel reads B (IDKPT_TEX_FLAG_R_FROM_B), bit 9: MagFilter NEAREST
 };
 
 // ---- material textures: texture(sampler2D, uv) at lod 0 = bilinear on the base level, evaluated explicitly in fp32
@@ -128,6 +128,8 @@ __device__ __forceinline__ float4 tex_sample_raw(const TexRec* textures, const f
     const TexRec& t = textures[handle - 1];
     if (t.wrapS == 10497) u = u - floorf(u);
     if (t.wrapT == 10497) v = v - floorf(v);
+    if (t.kind & 512)             // GL_NEAREST magnification: the texel that contains (u, v)
+        return tex_fetch(t, lut, tex_wrap((int)floorf(u * (float)t.w), t.w, t.wrapS), tex_wrap((int)floorf(v * (float)t.h), t.h, t.wrapT));
     const float px = u * (float)t.w - 0.5f, py = v * (float)t.h - 0.5f;
     const float fx0 = floorf(px), fy0 = floorf(py);
     const float fx = px - fx0, fy = py - fy0;

@@ -37,7 +37,7 @@ static inline const char* idk_validate_textures(const IdkPtSceneDesc* s) {
         const IdkPtTextureDesc& t = s->Textures[i];
         if (!t.Pixels || t.Width < 1 || t.Height < 1 || t.Width > 16384 || t.Height > 16384) return "texture without pixels or with an invalid size";
         if (idk_tex_kind(t.Format) < 0) return "texture format not supported (RGBA8 unorm / sRGB, BC7, BC5, BC4, R/RG/RGBA32F)";
-        if (t.Flags & ~IDKPT_TEX_FLAG_R_FROM_B) return "unknown texture flag";
+        if (t.Flags & ~(IDKPT_TEX_FLAG_R_FROM_B | IDKPT_TEX_FLAG_MAG_NEAREST)) return "unknown texture flag";
         for (int k = 0; k < 2; k++) {
             const int wm = k ? t.WrapT : t.WrapS;
             if (wm != 10497 && wm != 33071 && wm != 33648) return "texture wrap mode must be REPEAT, CLAMP_TO_EDGE or MIRRORED_REPEAT";
@@ -92,7 +92,7 @@ static inline cudaError_t idk_upload_texture_table(const IdkPtTextureDesc* textu
         recs[i].px = dst;
         recs[i].w = t.Width; recs[i].h = t.Height; recs[i].wrapS = t.WrapS; recs[i].wrapT = t.WrapT;
         recs[i].srgb = (t.Format == IDKPT_TEX_RGBA8_SRGB || t.Format == IDKPT_TEX_BC7_SRGB) ? 1 : 0;
-        recs[i].kind = kind | ((t.Flags & IDKPT_TEX_FLAG_R_FROM_B) ? 256 : 0);
+        recs[i].kind = kind | ((t.Flags & IDKPT_TEX_FLAG_R_FROM_B) ? 256 : 0) | ((t.Flags & IDKPT_TEX_FLAG_MAG_NEAREST) ? 512 : 0);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
     if (staging) cudaFree(staging);

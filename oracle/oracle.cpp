@@ -658,6 +658,8 @@ static Vec4 TexSample(const IdkPtSceneDesc& d, uint64_t handle, float u, float v
     const IdkPtTextureDesc& t = d.Textures[handle - 1];
     if (t.WrapS == 10497) u = u - floorf(u);
     if (t.WrapT == 10497) v = v - floorf(v);
+    if (t.Flags & IDKPT_TEX_FLAG_MAG_NEAREST)      // lod 0 = magnification: the sampler's MagFilter applies (ModelLoader.cs:1166-1196); NEAREST = the containing texel
+        return TexFetch(t, TexWrap((int)floorf(u * (float)t.Width), t.Width, t.WrapS), TexWrap((int)floorf(v * (float)t.Height), t.Height, t.WrapT));
     const float px = u * (float)t.Width - 0.5f, py = v * (float)t.Height - 0.5f;
     const float fx0 = floorf(px), fy0 = floorf(py);
     const float fx = px - fx0, fy = py - fy0;

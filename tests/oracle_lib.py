@@ -132,10 +132,10 @@ def post_process(result, settings=None, want_bloom=False, threads=None):
     return (out, bloom) if want_bloom else out
 
 
-def tex_sample(pixels, uv, srgb=False, wrap_s=10497, wrap_t=10497):
+def tex_sample(pixels, uv, srgb=False, wrap_s=10497, wrap_t=10497, flags=0):
     px = np.ascontiguousarray(pixels, np.uint8)
     uv = np.ascontiguousarray(uv, np.float32)
-    t = capi.IdkPtTextureDesc(px.ctypes.data, px.shape[1], px.shape[0], 1 if srgb else 0, wrap_s, wrap_t, 0)
+    t = capi.IdkPtTextureDesc(px.ctypes.data, px.shape[1], px.shape[0], 1 if srgb else 0, wrap_s, wrap_t, flags)
     out = np.zeros((len(uv), 4), np.float32)
     L = lib()
     L.oracle_tex_sample.restype = None

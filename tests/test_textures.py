@@ -54,6 +54,32 @@ def test_oracle_sampling_matches_gl_rules(srgb, wrap_s, wrap_t):
     assert np.allclose(c, px[2, 3] / 255.0, atol=1e-6)
 
 
+@pytest.mark.parametrize("wrap_s,wrap_t", [(10497, 33071), (33648, 10497)])
+def test_oracle_nearest_magnification(wrap_s, wrap_t):
+    """IDKPT_TEX_FLAG_MAG_NEAREST (glTF magFilter 9728): at lod 0 the sample is the texel that contains (u, v) after wrapping."""
+    rng = np.random.default_rng(6)
+    px = rng.integers(0, 256, (5, 9, 4)).astype(np.uint8)
+    uv = rng.uniform(-2.5, 3.5, (3000, 2)).astype(np.float32)
+    got = ol.tex_sample(px, uv, False, wrap_s, wrap_t, flags=capi.IDKPT_TEX_FLAG_MAG_NEAREST)
+
+    def wrap(i, n, mode):
+        if mode == 33071:
+            return np.clip(i, 0, n - 1)
+        if mode == 33648:
+            m = np.mod(i, 2 * n)
+            return np.where(m < n, m, 2 * n - 1 - m)
+        return np.mod(i, n)
+    u, v = uv[:, 0].astype(np.float64), uv[:, 1].astype(np.float64)
+    if wrap_s == 10497:
+        u = (uv[:, 0] - np.floor(uv[:, 0])).astype(np.float64)
+    if wrap_t == 10497:
+        v = (uv[:, 1] - np.floor(uv[:, 1])).astype(np.float64)
+    x = wrap(np.floor(u.astype(np.float32) * np.float32(9)).astype(int), 9, wrap_s)
+    y = wrap(np.floor(v.astype(np.float32) * np.float32(5)).astype(int), 5, wrap_t)
+    assert np.array_equal(got, (px[y, x].astype(np.float32) / np.float32(255.0)))
+    assert len(np.unique(got.round(6), axis=0)) <= 45          # only texel values, nothing in between
+
+
 def test_oracle_textures_change_the_image(textured):
     scene, cam = textured
     w, h = 80, 60
@@ -220,10 +246,11 @@ def compressed_variants(scene):
             blocks = bcn_ref.encode_texture("bc4", px[..., :1])
             gpu.textures.append(dict(format=capi.IDKPT_TEX_BC4_R_UNORM, width=w, height=h, data=blocks, **common))
             cpu.textures.append(dict(format=capi.IDKPT_TEX_R32F, width=w, height=h, data=bcn_ref.decode_texture("bc4", blocks, w, h), **common))
-        else:               # base colour / emissive -> BC7 sRGB
+        else:               # base colour / emissive -> BC7 sRGB; the floor's sampler asks for NEAREST magnification
             blocks = bcn_ref.encode_texture("bc7", px)
-            gpu.textures.append(dict(format=capi.IDKPT_TEX_BC7_SRGB if t["srgb"] else capi.IDKPT_TEX_BC7_UNORM, width=w, height=h, data=blocks, **common))
-            cpu.textures.append(dict(pixels=bcn_ref.decode_texture("bc7", blocks, w, h), srgb=t["srgb"], **common))
+            fl = capi.IDKPT_TEX_FLAG_MAG_NEAREST if k == 0 else 0
+            gpu.textures.append(dict(format=capi.IDKPT_TEX_BC7_SRGB if t["srgb"] else capi.IDKPT_TEX_BC7_UNORM, width=w, height=h, data=blocks, flags=fl, **common))
+            cpu.textures.append(dict(pixels=bcn_ref.decode_texture("bc7", blocks, w, h), srgb=t["srgb"], flags=fl, **common))
     return gpu, cpu
 
 
