@@ -80,7 +80,8 @@ class IdkPtStats(ctypes.Structure):
 
 
 IDKPT_IMAGE_RESULT, IDKPT_IMAGE_ALBEDO, IDKPT_IMAGE_NORMAL, IDKPT_IMAGE_GATHERED, IDKPT_IMAGE_DENOISED = 0, 1, 2, 3, 4
-IDKPT_GATHER_HANDLE_BYTES = 256
+IDKPT_GATHER_HANDLE_BYTES = 320
+IDKPT_CREATE_GLOBAL_SLOTS = 1 << 12
 IDKPT_ARRAY_MESH_TRANSFORMS, IDKPT_ARRAY_MESHES, IDKPT_ARRAY_MATERIALS, IDKPT_ARRAY_LIGHTS = 0, 1, 2, 3
 IDKPT_ARRAY_TLAS_NODES, IDKPT_ARRAY_BLAS_NODES, IDKPT_ARRAY_VERTEX_POSITIONS, IDKPT_ARRAY_VERTICES = 4, 5, 6, 7
 
@@ -90,7 +91,7 @@ EXPORTS = [
     "idkpt_resize", "idkpt_reset_accumulation", "idkpt_accumulated_samples", "idkpt_set_accumulated_samples",
     "idkpt_compute", "idkpt_sync", "idkpt_stream_handle", "idkpt_read_result", "idkpt_write_result", "idkpt_present_async", "idkpt_present_wait",
     "idkpt_register_host_buffer", "idkpt_unregister_host_buffer",
-    "idkpt_gather_export", "idkpt_gather_import", "idkpt_gather_device_ptr",
+    "idkpt_gather_export", "idkpt_gather_import", "idkpt_gather_connect", "idkpt_gather_device_ptr",
     "idkpt_result_device_ptr", "idkpt_tile_rows",
     "idkpt_read_wavefront_rays", "idkpt_trace_rays", "idkpt_trace_rays_any", "idkpt_shadows_ray_traced",
     "idkpt_set_skinning_data", "idkpt_skin_vertices", "idkpt_blas_refit", "idkpt_read_range", "idkpt_post_process", "idkpt_ldr_device_ptr", "idkpt_abi_version",
@@ -254,6 +255,8 @@ def load(path=None):
     L.idkpt_gather_export.argtypes = [c_vp, c_vp, c_u64]
     L.idkpt_gather_import.restype = c_i32
     L.idkpt_gather_import.argtypes = [c_vp, c_i32, c_i32, c_vp, c_u64]
+    L.idkpt_gather_connect.restype = c_i32
+    L.idkpt_gather_connect.argtypes = [c_vp, c_i32]
     L.idkpt_gather_device_ptr.restype = c_i32
     L.idkpt_gather_device_ptr.argtypes = [c_vp, P(c_vp), P(c_u64)]
     L.idkpt_result_device_ptr.restype = c_i32

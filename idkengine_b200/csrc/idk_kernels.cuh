@@ -1064,6 +1064,8 @@ struct ShadeArgs {
     float4* radiance;              // per tile pixel: final radiance (w = traversal cost)
     float4* aovAlbedoFinal;        // per tile pixel (AOVs only)
     float4* aovNormalFinal;
+    const uint32_t* slotDelta;     // multi-GPU global slots (k_slot_exchange): per local stripe, global slot - local slot; null = local slots
+    uint32_t stripePixels;         // pixels per stripe (stripe height x width)
     int exportState;               // debug export: terminated paths also write their final state back
     int firstHit;
     int lastBounce;                // survivors are final: no compaction
@@ -1107,8 +1109,11 @@ __global__ void __launch_bounds__(IDK_BLOCK, IDK_SHADE_MIN_BLOCKS) k_shade(Shade
                 st.rx = v3.x; st.ry = v3.y; st.rz = v3.z; st.pad = 0;
             }
             if (a.outputAovs && !a.firstHit) { aov0 = a.aov[2 * (size_t)src]; aov1 = a.aov[2 * (size_t)src + 1]; }
-            uint32_t rng = a.firstHit ? st.rng : (gid * 4096u + f.accumulatedSamples);
-            const uint32_t reseed = a.firstHit ? st.reseed : gid;   // gl_GlobalInvocationID.y*4096 + .x
+            // NHit's gl_GlobalInvocationID.x is the ray's slot in the alive list of the WHOLE image; a stripe tile adds the number of
+            // alive rays in the other ranks' stripes above it (k_slot_exchange), so that N GPUs draw the 1-GPU random numbers
+            const uint32_t slot = (a.slotDelta && !a.firstHit) ? gid + a.slotDelta[src / a.stripePixels] : gid;
+            uint32_t rng = a.firstHit ? st.rng : (slot * 4096u + f.accumulatedSamples);
+            const uint32_t reseed = a.firstHit ? st.reseed : slot;   // gl_GlobalInvocationID.y*4096 + .x
 
             const float4 hv = reinterpret_cast<const float4*>(a.hits)[gid];
             const float hitT = hv.z;
@@ -1460,6 +1465,84 @@ struct GatherArgs {
 __global__ void __launch_bounds__(IDK_BLOCK) k_accumulate_scatter(const float4* __restrict__ radiance, float4* __restrict__ result,
                                                                   uint32_t count, uint32_t accumulatedSamples, int debugTraversal,
                                                                   GatherArgs g);
+
+// Multi-GPU "global slots" (SURVEY 8e option ii): NHit seeds its random numbers with the ray's slot in the alive list
+// (NHit/compute.glsl: gl_GlobalInvocationID.x), and in the canonical (ascending pixel) order that slot counts the alive rays of
+// the WHOLE image below it. A stripe tile knows only its own rays, so once per bounce the ranks exchange their per-stripe
+// alive counts over NVLink peer memory -- one 8-byte word per stripe, written straight into every peer's table, tagged with
+// the exchange epoch -- and every rank prefix-sums the full table: global slot = local slot + delta[local stripe]. With this
+// the N-GPU image is bit-identical to the 1-GPU image. One CTA; the alive list is ascending, so the stripe boundaries are
+// binary searches. Double-buffered by epoch parity: a rank can be at most one exchange ahead of the slowest peer, because
+// finishing exchange e needs every peer's word e, which a peer publishes only after it has finished reading e - 1.
+#define IDK_MAX_STRIPES 4096
+struct SlotExchangeArgs {
+    const uint32_t* alive;                          // this bounce's alive list (ascending tile pixel)
+    const uint32_t* count;
+    unsigned long long* peerTable[IDK_MAX_PEERS];   // this lane's table of epoch parity `epoch & 1` on every rank: [nStripes] words
+    uint32_t* delta;                                // out: [nLocalStripes]
+    uint32_t* timedOut;
+    long long timeoutCycles;
+    uint32_t epoch;
+    int world, rank;
+    uint32_t stripePixels, nLocalStripes, nStripes;
+};
+
+__global__ void __launch_bounds__(256) k_slot_exchange(SlotExchangeArgs a) {
+    __shared__ uint32_t s_val[IDK_MAX_STRIPES + 1];   // local stripe starts, then the global per-stripe counts / bases
+    __shared__ uint32_t s_start[IDK_MAX_STRIPES / 2 + 2];
+    __shared__ uint32_t s_part[256];
+    const uint32_t count = *a.count;
+    const uint32_t tid = threadIdx.x;
+    // first alive-list index whose pixel lies in local stripe t or above
+    for (uint32_t t = tid; t <= a.nLocalStripes; t += blockDim.x) {
+        uint32_t lo = 0, hi = count;
+        if (t == a.nLocalStripes) lo = count;
+        else {
+            const uint32_t firstPixel = t * a.stripePixels;
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                if (a.alive[mid] < firstPixel) lo = mid + 1; else hi = mid;
+            }
+        }
+        s_start[t] = lo;
+    }
+    __syncthreads();
+    // publish: local stripe t is global stripe t * world + rank
+    for (uint32_t t = tid; t < a.nLocalStripes; t += blockDim.x) {
+        const unsigned long long word = ((unsigned long long)a.epoch << 32) | (unsigned long long)(s_start[t + 1] - s_start[t]);
+        for (int p = 0; p < a.world; p++) *((volatile unsigned long long*)&a.peerTable[p][t * (uint32_t)a.world + (uint32_t)a.rank]) = word;
+    }
+    __threadfence_system();
+    // collect every stripe's count of this epoch
+    const unsigned long long* mine = a.peerTable[a.rank];
+    const long long t0 = clock64();
+    for (uint32_t s = tid; s < a.nStripes; s += blockDim.x) {
+        unsigned long long w;
+        for (;;) {
+            w = *((volatile const unsigned long long*)&mine[s]);
+            if ((uint32_t)(w >> 32) == a.epoch) break;
+            if (clock64() - t0 > a.timeoutCycles) { *a.timedOut = 2u; w = 0; break; }   // a peer died: fail (idkpt_sync reports it) instead of hanging
+        }
+        s_val[s] = (uint32_t)w;
+    }
+    __syncthreads();
+    // exclusive prefix sum over the stripes in image order: each thread owns a contiguous chunk
+    const uint32_t chunk = (a.nStripes + blockDim.x - 1) / blockDim.x;
+    const uint32_t c0 = min(tid * chunk, a.nStripes), c1 = min(c0 + chunk, a.nStripes);
+    uint32_t sum = 0;
+    for (uint32_t s = c0; s < c1; s++) sum += s_val[s];
+    s_part[tid] = sum;
+    __syncthreads();
+    if (tid == 0) {
+        uint32_t run = 0;
+        for (uint32_t i = 0; i < blockDim.x; i++) { const uint32_t v = s_part[i]; s_part[i] = run; run += v; }
+    }
+    __syncthreads();
+    uint32_t run = s_part[tid];
+    for (uint32_t s = c0; s < c1; s++) { const uint32_t v = s_val[s]; s_val[s] = run; run += v; }
+    __syncthreads();
+    for (uint32_t t = tid; t < a.nLocalStripes; t += blockDim.x) a.delta[t] = s_val[t * (uint32_t)a.world + (uint32_t)a.rank] - s_start[t];
+}
 
 // timeoutCycles: SM clocks (idkpt.cu: IDKPT_GATHER_TIMEOUT_MS, default 30 s). Peers only have to have called
 // idkpt_gather_import before their first gathered Compute; a rank that is still uploading its scene just makes the others

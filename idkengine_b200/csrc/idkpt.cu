@@ -18,7 +18,8 @@
 #include "idk_post.cuh"
 #include "idk_textures_host.h"
 
-#define IDKPT_ABI_VERSION 3u   // 2: IdkPtSceneDesc gained Textures / TextureCount; 3: IdkPtStats gained CompactMs / AccumulateMs, host-buffer registration
+#define IDKPT_ABI_VERSION 4u   // 2: IdkPtSceneDesc gained Textures / TextureCount; 3: IdkPtStats gained CompactMs / AccumulateMs, host-buffer registration;
+                               // 4: gather handle blob is 5 IPC handles (320 bytes), IDKPT_CREATE_GLOBAL_SLOTS, idkpt_gather_connect
 
 static thread_local std::string g_createError;
 
@@ -42,6 +43,8 @@ struct Lane {
     uint32_t epoch = 0;            // compaction epoch of this lane's status words: 1 .. IDK_EPOCH_MASK, cleared on wrap
     DevBuf keys;                   // ray sorting: key per slot of the compacted alive list
     IdkSortScratch sortScratch;
+    DevBuf slotDelta;              // global slots: per local stripe, global - local slot of the current bounce (k_slot_exchange)
+    uint32_t slotEpoch = 0;        // exchanges issued on this lane since the peers were connected (identical on every rank)
 };
 
 struct IdkPtCtx {
@@ -123,6 +126,12 @@ struct IdkPtCtx {
     double gatherTimeoutMs = 30000.0;                                     // arrival wait bound (IDKPT_GATHER_TIMEOUT_MS); a dead peer becomes an error, not a hung GPU
     int clockKHz = 1965000;
     int gatherCurrent = -1;                                               // buffer holding the last completed frame
+    bool peerIsIpc = false;                                               // peers mapped with cudaIpcOpenMemHandle (else: same-process pointers)
+    // global slots (IDKPT_CREATE_GLOBAL_SLOTS): per-stripe alive counts exchanged every bounce; table = [lane][parity][stripe] u64
+    bool globalSlots = false;
+    int nStripes = 0, nLocalStripes = 0;
+    DevBuf slotTable;                                                     // own table (exported)
+    void* peerSlotTable[IDK_MAX_PEERS] = {};
 
     // asynchronous presentation (device snapshot + D2H on a second stream, overlapping the next Compute)
     cudaStream_t copyStream = nullptr;
@@ -175,6 +184,10 @@ static void compute_tile_rows(IdkPtCtx* ctx) {
     for (int y = 0; y < ctx->height; y++)
         if (ctx->tileCount <= 1 || ((y / ctx->stripeH) % ctx->tileCount) == ctx->tileIndex) ctx->rows.push_back(y);
     ctx->nLocal = (uint32_t)(ctx->rows.size() * (size_t)ctx->width);
+    ctx->nStripes = (ctx->height + ctx->stripeH - 1) / ctx->stripeH;
+    ctx->nLocalStripes = 0;
+    for (int s = 0; s < ctx->nStripes; s++)
+        if (ctx->tileCount <= 1 || (s % ctx->tileCount) == ctx->tileIndex) ctx->nLocalStripes++;
 }
 
 static int configure_launches(IdkPtCtx* ctx) {
@@ -274,6 +287,7 @@ static int allocate_lane(IdkPtCtx* ctx, Lane& ln) {
     CK(ensure(ln.countsDev, (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
     CK(ensure(ln.tickets, 2 * (IDKPT_MAX_RAY_DEPTH + 1) * sizeof(uint32_t)));
     CK(ensure(ln.tileStatus, ((n + IDK_BLOCK * IDK_COMPACT_ITEMS - 1) / (IDK_BLOCK * IDK_COMPACT_ITEMS) + 1) * sizeof(unsigned long long)));
+    if (ctx->globalSlots && ctx->tileCount > 1) CK(ensure(ln.slotDelta, (size_t)std::max(1, ctx->nLocalStripes) * sizeof(uint32_t)));
     CK(cudaMemsetAsync(ln.tileStatus.p, 0, ln.tileStatus.bytes, ctx->stream));
     if (!ln.stream) CK(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
     if (!ln.radianceReady) CK(cudaEventCreateWithFlags(&ln.radianceReady, cudaEventDisableTiming));
@@ -288,7 +302,7 @@ static int allocate_lane(IdkPtCtx* ctx, Lane& ln) {
 
 static void release_lane(Lane& ln, bool keepStream) {
     DevBuf* all[] = {&ln.state, &ln.aov, &ln.alive[0], &ln.alive[1], &ln.survivors, &ln.keysTmp, &ln.sortedAlive, &ln.hits, &ln.hitXform, &ln.debugCost,
-                     &ln.radiance, &ln.aovAlbedoFinal, &ln.aovNormalFinal, &ln.countsDev, &ln.tickets, &ln.tileStatus, &ln.keys};
+                     &ln.radiance, &ln.aovAlbedoFinal, &ln.aovNormalFinal, &ln.countsDev, &ln.tickets, &ln.tileStatus, &ln.keys, &ln.slotDelta};
     for (DevBuf* b : all) release(*b);
     idk_sort_release(ln.sortScratch);
     ln.allocated = false;
@@ -324,7 +338,8 @@ static int check_device_errors(IdkPtCtx* ctx, cudaError_t se, const char* who) {
         CK(cudaMemcpy(&timedOut, (uint32_t*)ctx->gatherScratch.p + 1, 4, cudaMemcpyDeviceToHost));
         if (timedOut) {
             cudaMemset((uint32_t*)ctx->gatherScratch.p + 1, 0, 4);
-            return fail(ctx, IDKPT_ERR_CUDA, "idkpt_compute: timed out waiting for a peer rank's tile (multi-GPU gather)");
+            return fail(ctx, IDKPT_ERR_CUDA, timedOut == 2u ? "idkpt_compute: timed out waiting for a peer rank's per-stripe alive counts (multi-GPU global slots)"
+                                                            : "idkpt_compute: timed out waiting for a peer rank's tile (multi-GPU gather)");
         }
     }
     return IDKPT_OK;
@@ -471,14 +486,21 @@ static int tlas_height(const GpuTlasNode* t, uint64_t count) {
 static void gather_teardown(IdkPtCtx* ctx) {
     for (int b = 0; b < 2; b++)
         for (int p = 0; p < IDK_MAX_PEERS; p++) {
-            if (ctx->peerMapped[p] && p != ctx->gatherRank) {
+            if (ctx->peerMapped[p] && p != ctx->gatherRank && ctx->peerIsIpc) {
                 if (ctx->peerImage[b][p]) cudaIpcCloseMemHandle(ctx->peerImage[b][p]);
                 if (ctx->peerFlags[b][p]) cudaIpcCloseMemHandle(ctx->peerFlags[b][p]);
             }
             ctx->peerImage[b][p] = nullptr;
             ctx->peerFlags[b][p] = nullptr;
         }
-    for (int p = 0; p < IDK_MAX_PEERS; p++) ctx->peerMapped[p] = false;
+    for (int p = 0; p < IDK_MAX_PEERS; p++) {
+        if (ctx->peerMapped[p] && p != ctx->gatherRank && ctx->peerIsIpc && ctx->peerSlotTable[p]) cudaIpcCloseMemHandle(ctx->peerSlotTable[p]);
+        ctx->peerSlotTable[p] = nullptr;
+        ctx->peerMapped[p] = false;
+    }
+    ctx->peerIsIpc = false;
+    release(ctx->slotTable);
+    for (int i = 0; i < IDK_MAX_LANES; i++) ctx->lanes[i].slotEpoch = 0;
     for (int b = 0; b < 2; b++) { release(ctx->gatherImage[b]); release(ctx->gatherFlags[b]); }
     release(ctx->gatherRows);
     release(ctx->gatherScratch);
@@ -500,6 +522,8 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
         return fail(nullptr, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_create: invalid image size");
     int stripe = ci->TileStripeHeight > 0 ? ci->TileStripeHeight : 8;
     int tcount = ci->TileCount > 1 ? ci->TileCount : 1;
+    if ((ci->Flags & IDKPT_CREATE_GLOBAL_SLOTS) && tcount > 1 && (ci->Height + stripe - 1) / stripe > IDK_MAX_STRIPES)
+        return fail(nullptr, IDKPT_ERR_UNSUPPORTED, "idkpt_create: IDKPT_CREATE_GLOBAL_SLOTS supports at most 4096 stripes (raise TileStripeHeight)");
     if (tcount > 1 && (ci->TileIndex < 0 || ci->TileIndex >= tcount))
         return fail(nullptr, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_create: TileIndex out of range");
     int deviceCount = 0;
@@ -536,6 +560,7 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
     if (const char* v = getenv("IDKPT_PACK_ASYNC")) ctx->packAsync = atoi(v) != 0;
     if (const char* v = getenv("IDKPT_PACK_CTA")) ctx->packCta = std::max(0, atoi(v));
     if (const int fl = (ci->Flags >> 8) & 15) ctx->laneCount = std::min(IDK_MAX_LANES, fl);   // IDKPT_CREATE_LANES(n)
+    ctx->globalSlots = (ci->Flags & IDKPT_CREATE_GLOBAL_SLOTS) != 0;
     if (const char* v = getenv("IDKPT_LANES")) ctx->laneCount = std::max(1, std::min(IDK_MAX_LANES, atoi(v)));
     if (const char* v = getenv("IDKPT_DEBUG_EPOCH_START")) ctx->epochStart = (uint32_t)strtoul(v, nullptr, 0) & IDK_EPOCH_MASK;
     if (const char* v = getenv("IDKPT_GATHER_TIMEOUT_MS")) ctx->gatherTimeoutMs = std::max(1.0, atof(v));
@@ -842,6 +867,8 @@ IDKPT_API int idkpt_resize(IdkPtCtx* ctx, int32_t width, int32_t height) {
     if (!ctx) return IDKPT_ERR_INVALID_ARGUMENT;
     DRAIN_PENDING("idkpt_resize");
     if (width <= 0 || height <= 0 || width > 16384 || height > 16384) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_resize: invalid size");
+    if (ctx->globalSlots && ctx->tileCount > 1 && (height + ctx->stripeH - 1) / ctx->stripeH > IDK_MAX_STRIPES)
+        return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_resize: IDKPT_CREATE_GLOBAL_SLOTS supports at most 4096 stripes");
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     if (ctx->copyPending) { CK(cudaEventSynchronize(ctx->copyDone)); ctx->copyPending = false; }
@@ -946,6 +973,11 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
     // (idkpt_sync, or any call that reads device data, waits). With stats the call is synchronous and runs one sample at
     // a time on lane 0, exactly the sequence the per-kernel timings describe.
     const bool async = stats == nullptr && !wantStats && !ctx->exportEnabled && ctx->laneCount > 1;
+    const bool globalSlots = ctx->globalSlots && ctx->tileCount > 1;
+    if (globalSlots && ctx->gatherWorld < 2)
+        return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_compute: IDKPT_CREATE_GLOBAL_SLOTS needs the peers connected (idkpt_gather_import / idkpt_gather_connect)");
+    if (globalSlots && sorting)
+        return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_compute: ray sorting reorders the slots by a tile-local key sort; not available with IDKPT_CREATE_GLOBAL_SLOTS");
     if (!async && ctx->asyncPending) {
         int rc = check_device_errors(ctx, drain(ctx), "idkpt_compute");
         if (rc) return rc;
@@ -1017,6 +1049,26 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                 alive = (const uint32_t*)ln.sortedAlive.p;
             }
 
+            if (globalSlots && !first) {
+                // per-stripe alive counts of this bounce to every peer, everybody's counts back: global slot = local slot + delta[stripe]
+                SlotExchangeArgs xa;
+                memset(&xa, 0, sizeof(xa));
+                const uint32_t epoch = ++ln.slotEpoch;   // 32 bits: ~20 days at 2,400 exchanges per second and lane
+                const size_t laneIdx = (size_t)(&ln - ctx->lanes);
+                for (int p = 0; p < ctx->gatherWorld; p++)
+                    xa.peerTable[p] = (unsigned long long*)ctx->peerSlotTable[p] + (laneIdx * 2 + (epoch & 1u)) * (size_t)ctx->nStripes;
+                xa.alive = alive; xa.count = counts + j;
+                xa.delta = (uint32_t*)ln.slotDelta.p;
+                xa.timedOut = (uint32_t*)ctx->gatherScratch.p + 1;
+                xa.timeoutCycles = (long long)(ctx->gatherTimeoutMs * (double)ctx->clockKHz);
+                xa.epoch = epoch;
+                xa.world = ctx->gatherWorld; xa.rank = ctx->gatherRank;
+                xa.stripePixels = (uint32_t)ctx->stripeH * (uint32_t)ctx->width;
+                xa.nLocalStripes = (uint32_t)ctx->nLocalStripes; xa.nStripes = (uint32_t)ctx->nStripes;
+                k_slot_exchange<<<1, 256, 0, ls>>>(xa);
+                launches++;
+            }
+
             TraverseArgs ta;
             ta.sc = ctx->sc;
             ta.state = (const PathState*)ln.state.p;
@@ -1068,6 +1120,8 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
             sa.radiance = (float4*)ln.radiance.p;
             sa.aovAlbedoFinal = (float4*)ln.aovAlbedoFinal.p;
             sa.aovNormalFinal = (float4*)ln.aovNormalFinal.p;
+            sa.slotDelta = (globalSlots && !first) ? (const uint32_t*)ln.slotDelta.p : nullptr;
+            sa.stripePixels = (uint32_t)ctx->stripeH * (uint32_t)ctx->width;
             sa.exportState = ctx->exportEnabled ? 1 : 0;
             sa.firstHit = first ? 1 : 0;
             sa.lastBounce = last ? 1 : 0;
@@ -1316,27 +1370,68 @@ IDKPT_API int idkpt_unregister_host_buffer(IdkPtCtx* ctx, void* hostPtr) {
 // ---- multi-GPU gather over peer memory -----------------------------------------------------------------------------
 // Step 1 (every rank): allocate the exported buffers and return their CUDA IPC handles (4 x 64 bytes:
 // image[0], image[1], flags[0], flags[1]). Step 2: exchange the handles (any transport) and import all ranks' handles.
-IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handlesOut, uint64_t bytes) {
-    if (!ctx || !handlesOut) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_export: null argument");
-    DRAIN_PENDING("idkpt_gather_export");
-    if (bytes < 4 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_export: need 256 bytes");
-    CK(cudaSetDevice(ctx->device));
+// The buffers peers write into: full-size images + arrival flags (double-buffered), the per-stripe count tables of the
+// global-slot exchange. Stand-alone cudaMalloc allocations (IPC export needs that).
+// CUDA loads kernels lazily, and loading one may have to wait for the kernels that are running. Once contexts wait for each
+// other ON THE DEVICE (arrival wait, slot exchange) a first launch from the host thread that still has to submit the peer's
+// work would deadlock against them -- so everything a connected context can launch is loaded before the first wait exists.
+__global__ void k_denoise_import(const float* __restrict__ rgb, float4* __restrict__ out, int count);
+static int preload_kernels(IdkPtCtx* ctx) {
+    cudaFuncAttributes fa;
+#define IDK_PRELOAD(k) CK(cudaFuncGetAttributes(&fa, k))
+    IDK_PRELOAD(k_init_sample); IDK_PRELOAD(k_prepare_triangles); IDK_PRELOAD(k_prepare_vertices); IDK_PRELOAD(k_prepare_surfaces);
+    IDK_PRELOAD(k_raygen); IDK_PRELOAD(k_traverse<false>); IDK_PRELOAD(k_traverse<true>);
+    IDK_PRELOAD((k_traverse2<false, false, false>)); IDK_PRELOAD((k_traverse2<true, false, false>)); IDK_PRELOAD((k_traverse2<false, true, false>));
+    IDK_PRELOAD((k_traverse2<true, true, false>)); IDK_PRELOAD((k_traverse2<false, false, true>)); IDK_PRELOAD((k_traverse2<true, false, true>));
+    IDK_PRELOAD(k_shade<false>); IDK_PRELOAD(k_shade<true>); IDK_PRELOAD(k_compact); IDK_PRELOAD(k_slot_exchange);
+    IDK_PRELOAD(k_accumulate); IDK_PRELOAD(k_accumulate_aov); IDK_PRELOAD(k_accumulate_scatter); IDK_PRELOAD(k_gather_wait);
+    IDK_PRELOAD(k_sort_histogram); IDK_PRELOAD(k_sort_scan); IDK_PRELOAD(k_sort_scatter);
+    IDK_PRELOAD(k_trace_rays); IDK_PRELOAD(k_trace_rays_any); IDK_PRELOAD(k_shadows_ray_traced);
+    IDK_PRELOAD(k_skin_vertices); IDK_PRELOAD(k_refit_prepare); IDK_PRELOAD(k_refit_climb); IDK_PRELOAD(k_tlas_build);
+    IDK_PRELOAD(k_bloom_down); IDK_PRELOAD(k_bloom_up); IDK_PRELOAD(k_agx_matrices); IDK_PRELOAD(k_tonemap);
+    IDK_PRELOAD(k_denoise_prepare); IDK_PRELOAD(k_denoise_atrous); IDK_PRELOAD(k_denoise_finish); IDK_PRELOAD(k_denoise_import);
+    IDK_PRELOAD(k_bcn_decode);
+#undef IDK_PRELOAD
+    return IDKPT_OK;
+}
+
+static size_t slot_table_words(const IdkPtCtx* ctx) { return (size_t)IDK_MAX_LANES * 2 * (size_t)std::max(1, ctx->nStripes); }
+static int gather_allocate(IdkPtCtx* ctx) {
+    { int rc = preload_kernels(ctx); if (rc) return rc; }
     const size_t imgBytes = (size_t)ctx->width * ctx->height * 16;
-    cudaIpcMemHandle_t* out = (cudaIpcMemHandle_t*)handlesOut;
     for (int b = 0; b < 2; b++) {
-        // IPC export needs stand-alone cudaMalloc allocations
         CK(ensure(ctx->gatherImage[b], imgBytes));
         CK(ensure(ctx->gatherFlags[b], IDK_MAX_PEERS * sizeof(uint32_t)));
         CK(cudaMemsetAsync(ctx->gatherImage[b].p, 0, imgBytes, ctx->stream));
         CK(cudaMemsetAsync(ctx->gatherFlags[b].p, 0, IDK_MAX_PEERS * sizeof(uint32_t), ctx->stream));
-        CK(cudaIpcGetMemHandle(&out[b], ctx->gatherImage[b].p));
-        CK(cudaIpcGetMemHandle(&out[2 + b], ctx->gatherFlags[b].p));
     }
+    // every lane is brought up NOW: once peers wait for each other on the device, a later allocation (an implicit device
+    // synchronisation in the worst case) from the thread that still has to submit a peer's work could deadlock
+    if (ctx->laneCount > 1)
+        for (int i = 0; i < ctx->laneCount; i++)
+            if (!ctx->lanes[i].allocated) { int rc = allocate_lane(ctx, ctx->lanes[i]); if (rc) return rc; }
+    CK(ensure(ctx->slotTable, slot_table_words(ctx) * sizeof(unsigned long long)));
+    CK(cudaMemsetAsync(ctx->slotTable.p, 0, ctx->slotTable.bytes, ctx->stream));   // epoch 0 = nothing published
     CK(ensure(ctx->gatherScratch, 16));
     CK(cudaMemsetAsync(ctx->gatherScratch.p, 0, 16, ctx->stream));
     CK(ensure(ctx->gatherRows, std::max<size_t>(ctx->rows.size(), 1) * sizeof(int)));
     if (!ctx->rows.empty()) CK(cudaMemcpyAsync(ctx->gatherRows.p, ctx->rows.data(), ctx->rows.size() * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    return IDKPT_OK;
+}
+
+IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handlesOut, uint64_t bytes) {
+    if (!ctx || !handlesOut) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_export: null argument");
+    DRAIN_PENDING("idkpt_gather_export");
+    if (bytes < IDKPT_GATHER_HANDLE_BYTES) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_export: need IDKPT_GATHER_HANDLE_BYTES (320) bytes");
+    CK(cudaSetDevice(ctx->device));
+    { int rc = gather_allocate(ctx); if (rc) return rc; }
+    cudaIpcMemHandle_t* out = (cudaIpcMemHandle_t*)handlesOut;
+    for (int b = 0; b < 2; b++) {
+        CK(cudaIpcGetMemHandle(&out[b], ctx->gatherImage[b].p));
+        CK(cudaIpcGetMemHandle(&out[2 + b], ctx->gatherFlags[b].p));
+    }
+    CK(cudaIpcGetMemHandle(&out[4], ctx->slotTable.p));
     return IDKPT_OK;
 }
 
@@ -1346,26 +1441,78 @@ IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, co
     DRAIN_PENDING("idkpt_gather_import");
     if (world < 2 || world > IDK_MAX_PEERS || rank < 0 || rank >= world) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: invalid rank / world");
     if (world != ctx->tileCount || rank != ctx->tileIndex) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: rank / world must equal TileIndex / TileCount");
-    if (bytes < (uint64_t)world * 4 * sizeof(cudaIpcMemHandle_t)) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: handle buffer too small");
+    if (bytes < (uint64_t)world * IDKPT_GATHER_HANDLE_BYTES) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: handle buffer too small");
     if (!ctx->gatherImage[0].p) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: call idkpt_gather_export first");
+    if (ctx->gatherWorld > 1) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_import: peers are already connected (idkpt_resize disconnects them)");
     CK(cudaSetDevice(ctx->device));
     const cudaIpcMemHandle_t* hs = (const cudaIpcMemHandle_t*)allHandles;
+    ctx->peerIsIpc = true;
     for (int p = 0; p < world; p++) {
         for (int b = 0; b < 2; b++) {
             if (p == rank) {
                 ctx->peerImage[b][p] = ctx->gatherImage[b].p;
                 ctx->peerFlags[b][p] = ctx->gatherFlags[b].p;
             } else {
-                CK(cudaIpcOpenMemHandle(&ctx->peerImage[b][p], hs[4 * p + b], cudaIpcMemLazyEnablePeerAccess));
-                CK(cudaIpcOpenMemHandle(&ctx->peerFlags[b][p], hs[4 * p + 2 + b], cudaIpcMemLazyEnablePeerAccess));
+                CK(cudaIpcOpenMemHandle(&ctx->peerImage[b][p], hs[5 * p + b], cudaIpcMemLazyEnablePeerAccess));
+                CK(cudaIpcOpenMemHandle(&ctx->peerFlags[b][p], hs[5 * p + 2 + b], cudaIpcMemLazyEnablePeerAccess));
             }
         }
+        if (p == rank) ctx->peerSlotTable[p] = ctx->slotTable.p;
+        else CK(cudaIpcOpenMemHandle(&ctx->peerSlotTable[p], hs[5 * p + 4], cudaIpcMemLazyEnablePeerAccess));
         ctx->peerMapped[p] = true;
     }
     ctx->gatherWorld = world;
     ctx->gatherRank = rank;
     ctx->gatherEpoch = 0;
     ctx->gatherCurrent = -1;
+    for (int i = 0; i < IDK_MAX_LANES; i++) ctx->lanes[i].slotEpoch = 0;
+    return IDKPT_OK;
+}
+
+// The same wiring for a host that drives all GPUs from ONE process (the reference engine is a single process): contexts
+// [0, world) in tile order, each created with TileIndex = its position and TileCount = world. No IPC: the contexts hand each
+// other their device pointers; peer access between different devices is enabled here.
+IDKPT_API int idkpt_gather_connect(IdkPtCtx** ctxs, int32_t world) {
+    if (!ctxs || world < 2 || world > IDK_MAX_PEERS) return fail(ctxs && world > 0 ? ctxs[0] : nullptr, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_connect: invalid argument");
+    for (int r = 0; r < world; r++) {
+        IdkPtCtx* ctx = ctxs[r];
+        if (!ctx) return fail(ctxs[0], IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_connect: null context");
+        if (ctx->tileCount != world || ctx->tileIndex != r) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_connect: context r must have TileIndex r and TileCount world");
+        if (ctx->width != ctxs[0]->width || ctx->height != ctxs[0]->height || ctx->stripeH != ctxs[0]->stripeH || ctx->laneCount != ctxs[0]->laneCount ||
+            ctx->globalSlots != ctxs[0]->globalSlots)
+            return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_connect: contexts differ in size, stripe height, lanes or flags");
+        DRAIN_PENDING("idkpt_gather_connect");
+        if (ctx->gatherWorld > 1) return fail(ctx, IDKPT_ERR_INVALID_ARGUMENT, "idkpt_gather_connect: peers are already connected");
+        CK(cudaSetDevice(ctx->device));
+        int rc = gather_allocate(ctx);
+        if (rc) return rc;
+    }
+    for (int r = 0; r < world; r++) {
+        IdkPtCtx* ctx = ctxs[r];
+        CK(cudaSetDevice(ctx->device));
+        for (int p = 0; p < world; p++) {
+            if (ctxs[p]->device != ctx->device) {
+                int can = 0;
+                CK(cudaDeviceCanAccessPeer(&can, ctx->device, ctxs[p]->device));
+                if (!can) return fail(ctx, IDKPT_ERR_UNSUPPORTED, "idkpt_gather_connect: no peer access between two of the devices");
+                const cudaError_t e = cudaDeviceEnablePeerAccess(ctxs[p]->device, 0);
+                if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+                else CK(e);
+            }
+            for (int b = 0; b < 2; b++) {
+                ctx->peerImage[b][p] = ctxs[p]->gatherImage[b].p;
+                ctx->peerFlags[b][p] = ctxs[p]->gatherFlags[b].p;
+            }
+            ctx->peerSlotTable[p] = ctxs[p]->slotTable.p;
+            ctx->peerMapped[p] = true;
+        }
+        ctx->peerIsIpc = false;
+        ctx->gatherWorld = world;
+        ctx->gatherRank = r;
+        ctx->gatherEpoch = 0;
+        ctx->gatherCurrent = -1;
+        for (int i = 0; i < IDK_MAX_LANES; i++) ctx->lanes[i].slotEpoch = 0;
+    }
     return IDKPT_OK;
 }
 

@@ -20,11 +20,14 @@ class IdkPtError(RuntimeError):
 
 
 class PathTracer:
-    def __init__(self, width, height, settings=None, device=0, tile=(8, 0, 1), lib_path=None, lanes=0):
+    def __init__(self, width, height, settings=None, device=0, tile=(8, 0, 1), lib_path=None, lanes=0, global_slots=False):
+        """global_slots: IDKPT_CREATE_GLOBAL_SLOTS -- a tiled (multi-GPU) context numbers its alive rays over the WHOLE image, so the
+        N-GPU image is bit-identical to the 1-GPU image (needs EnablePeerGather / ConnectPeers)."""
         self._lib = capi.load(lib_path)
         self._ctx = ctypes.c_void_p()
         self._settings = settings or capi.default_settings()
-        ci = capi.IdkPtCreateInfo(device, width, height, tile[0], tile[1], tile[2], (int(lanes) & 15) << 8)   # IDKPT_CREATE_LANES
+        flags = ((int(lanes) & 15) << 8) | (capi.IDKPT_CREATE_GLOBAL_SLOTS if global_slots else 0)   # IDKPT_CREATE_LANES
+        ci = capi.IdkPtCreateInfo(device, width, height, tile[0], tile[1], tile[2], flags)
         rc = self._lib.idkpt_create(ctypes.byref(ci), ctypes.byref(self._ctx))
         if rc != 0:
             msg = self._lib.idkpt_last_error(None)
@@ -239,6 +242,15 @@ class PathTracer:
         assert len(blobs) == world and all(len(b) == capi.IDKPT_GATHER_HANDLE_BYTES for b in blobs)
         allh = (ctypes.c_uint8 * (world * capi.IDKPT_GATHER_HANDLE_BYTES)).from_buffer_copy(b"".join(blobs))
         self._check(self._lib.idkpt_gather_import(self._ctx, rank, world, allh, len(allh)), "idkpt_gather_import")
+
+    @staticmethod
+    def ConnectPeers(tracers):
+        """Single-process multi-GPU: wire the tile contexts (in tile order) to each other without IPC (idkpt_gather_connect)."""
+        arr = (ctypes.c_void_p * len(tracers))(*[t._ctx.value for t in tracers])
+        rc = tracers[0]._lib.idkpt_gather_connect(arr, len(tracers))
+        if rc != 0:
+            msgs = [t._lib.idkpt_last_error(t._ctx) for t in tracers]
+            raise IdkPtError("idkpt_gather_connect failed (%d): %s" % (rc, "; ".join(m.decode() for m in msgs if m)))
 
     def GatheredDevicePtr(self):
         p, n = ctypes.c_void_p(), ctypes.c_uint64()

@@ -52,6 +52,13 @@ typedef enum IdkPtStatus {
  * image rows are cut into stripes of TileStripeHeight rows, stripe s belongs to
  * context (s % TileCount) == TileIndex. TileCount <= 1 => the whole image. */
 #define IDKPT_CREATE_LANES(n) (((uint32_t)(n) & 15u) << 8)
+/* Multi-GPU, strict parity: NHit seeds a ray's random numbers with its slot in the alive list (NHit/compute.glsl:
+ * gl_GlobalInvocationID.x). By default a tile numbers its own alive rays (the N-GPU image is then a valid, but different,
+ * Monte-Carlo estimate than the 1-GPU image, reproducible per GPU count). With this flag the ranks exchange their per-stripe
+ * alive counts over NVLink once per bounce so that every ray gets its WHOLE-IMAGE slot: the N-GPU image is bit-identical to
+ * the 1-GPU image. Needs the peers connected (idkpt_gather_import / idkpt_gather_connect) and every rank issuing the same
+ * idkpt_compute calls; not available together with DoRaySorting. Ignored when TileCount <= 1. */
+#define IDKPT_CREATE_GLOBAL_SLOTS (1u << 12)
 
 typedef struct IdkPtCreateInfo {
     int32_t Device;            /* CUDA device ordinal */
@@ -60,7 +67,7 @@ typedef struct IdkPtCreateInfo {
     int32_t TileStripeHeight;  /* rows per stripe (multiple of 8), 0 => 8 */
     int32_t TileIndex;
     int32_t TileCount;
-    uint32_t Flags;            /* 0, or IDKPT_CREATE_LANES(n): samples in flight for asynchronous idkpt_compute (default 8, 1 = off) */
+    uint32_t Flags;            /* 0, IDKPT_CREATE_LANES(n): samples in flight for asynchronous idkpt_compute (default 8, 1 = off), IDKPT_CREATE_GLOBAL_SLOTS */
 } IdkPtCreateInfo;
 
 /* Replaces the implicit SSBO bindings 4,5(vertices),8,9..: ModelManager.cs:103-119
@@ -238,14 +245,19 @@ IDKPT_API int idkpt_register_host_buffer(IdkPtCtx* ctx, void* host_ptr, uint64_t
 IDKPT_API int idkpt_unregister_host_buffer(IdkPtCtx* ctx, void* host_ptr);
 
 /* Multi-GPU tile gather over NVLink peer memory (no NCCL in the data path). Every rank calls idkpt_gather_export
- * (allocates a double-buffered full-size image + arrival flags and returns 4 CUDA IPC handles = 256 bytes), the ranks
+ * (allocates a double-buffered full-size image + arrival flags + the global-slot table and returns 5 CUDA IPC handles =
+ * 320 bytes; 4 handles / 256 bytes before ABI 4), the ranks
  * exchange the handles (torch.distributed, MPI, a socket...) and call idkpt_gather_import with all of them in rank
  * order. From then on the FinalDraw of every idkpt_compute also stores this rank's pixels into every rank's full image
  * at their final position and idkpt_compute returns once all ranks' tiles of that frame have arrived (or fails after
- * ~3 s if a peer never delivers). idkpt_resize drops the mappings: export / exchange / import again afterwards. */
-#define IDKPT_GATHER_HANDLE_BYTES 256
+ * IDKPT_GATHER_TIMEOUT_MS, default 30 s, if a peer never delivers). idkpt_resize drops the mappings: export / exchange /
+ * import again afterwards.
+ * idkpt_gather_connect does the same for a host that drives every GPU from ONE process (like the reference engine): pass
+ * the contexts in tile order (context r created with TileIndex r, TileCount world); no IPC, peer access is enabled here. */
+#define IDKPT_GATHER_HANDLE_BYTES 320
 IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handles_out, uint64_t bytes);
 IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, const void* all_handles, uint64_t bytes);
+IDKPT_API int idkpt_gather_connect(IdkPtCtx** ctxs, int32_t world);
 IDKPT_API int idkpt_gather_device_ptr(IdkPtCtx* ctx, void** dev_ptr, uint64_t* bytes);
 
 /* Device-side access for zero-copy hand-over (GL interop / NCCL gather):

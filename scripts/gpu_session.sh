@@ -2,6 +2,7 @@
 # One gpurun session; steps selected by arguments (default: tests probe). Everything lands in gpurun_out/.
 #   tests   pytest -m gpu            probe   scripts/variant_probe.py --run --eighth      sweep   probe + threshold sweep
 #   bench   python bench.py          ncu     launch list + --set full capture of the bench
+#   slots   strict multi-GPU parity in one process (scripts/check_global_slots.py)   slotsN  bench.py --global-slots on all GPUs
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/session_gpu.txt 2>&1
 steps="${@:-tests probe}"
@@ -26,6 +27,9 @@ for s in $steps; do
        ls -la gpurun_out/*.ncu-rep; tail -2 gpurun_out/ncu_t2.log;;
     sanitize) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize.py > gpurun_out/sanitize_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/sanitize_memcheck.log; tail -6 gpurun_out/sanitize_memcheck.log
        timeout 1500 compute-sanitizer --tool racecheck --error-exitcode 9 python scripts/sanitize.py > gpurun_out/sanitize_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/sanitize_racecheck.log; tail -4 gpurun_out/sanitize_racecheck.log;;
+    slots) for W in 2 3; do CUDA_DEVICE_MAX_CONNECTIONS=32 IDKPT_GATHER_TIMEOUT_MS=2000 timeout 200 python scripts/check_global_slots.py --world $W > gpurun_out/global_slots_w$W.json 2> gpurun_out/global_slots_w$W.err; rc=$?; echo "slots w$W exit $rc"; tail -3 gpurun_out/global_slots_w$W.err; cat gpurun_out/global_slots_w$W.json
+         if [ $rc -ne 0 ]; then CUDA_MODULE_LOADING=EAGER CUDA_DEVICE_MAX_CONNECTIONS=32 IDKPT_GATHER_TIMEOUT_MS=2000 timeout 200 python scripts/check_global_slots.py --world $W > gpurun_out/global_slots_w${W}_eager.json 2> gpurun_out/global_slots_w${W}_eager.err; echo "slots w$W eager exit $?"; tail -3 gpurun_out/global_slots_w${W}_eager.err; cat gpurun_out/global_slots_w${W}_eager.json; break; fi; done;;
+    slotsN) N=$(nvidia-smi -L | wc -l); timeout 1200 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29519 bench.py --gpus $N --global-slots > gpurun_out/bench_slots_n$N.json 2> gpurun_out/bench_slots_n$N.err; tail -5 gpurun_out/bench_slots_n$N.err; cut -c1-1500 gpurun_out/bench_slots_n$N.json;;
     smoke) timeout 600 python __graft_entry__.py --smoke 2>&1 | tail -3;;
     *) echo "unknown step $s";;
   esac

@@ -463,6 +463,25 @@ def test_multi_gpu_peer_gather():
     assert out.returncode == 0 and "PEER_GATHER_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
 
 
+@pytest.mark.parametrize("world", [2, 3])
+def test_global_slots_tiles_equal_one_gpu_image(world):
+    """SURVEY 8e option (ii), strict multi-GPU parity: `world` tile contexts with IDKPT_CREATE_GLOBAL_SLOTS, wired to each other
+    in one process by idkpt_gather_connect (so this runs on a single-GPU box, through the same peer-memory scatter / arrival
+    wait / per-bounce slot exchange kernels the multi-process path uses), reproduce the untiled image bit for bit -- in their
+    own rows and in every context's gathered frame -- while the default tile-local numbering does not."""
+    import json
+    import os
+    import subprocess
+    import sys
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", IDKPT_GATHER_TIMEOUT_MS="3000")   # fresh process: enough hardware queues for all streams
+    out = subprocess.run([sys.executable, os.path.join(repo, "scripts", "check_global_slots.py"), "--world", str(world)],
+                         capture_output=True, text=True, timeout=300, env=env)
+    assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-2500:]
+    rec = json.loads(out.stdout.strip().splitlines()[-1])
+    assert rec["ok"] and rec["tiles_eq_one_gpu"] and all(rec["gathered_eq_one_gpu"]) and rec["control_local_slots_differ"], rec
+
+
 # ---- scope table 8f.1: any-hit traversal and ray-traced shadows ---------------------------------------------------
 
 @pytest.mark.parametrize("name", ["cornell", "multi_blas", "atrium_small"])

@@ -29,7 +29,7 @@ def test_library_exports_every_declared_symbol(libidkpt):
     assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
     for name in declared:
         assert hasattr(libidkpt, name), name
-    assert libidkpt.idkpt_abi_version() == 3
+    assert libidkpt.idkpt_abi_version() == 4
 
 
 def test_host_library_exports_cache_symbols():
