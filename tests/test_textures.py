@@ -302,6 +302,6 @@ def test_gpu_rejects_malformed_texture_descs(textured):
     with PathTracer(32, 32) as pt:
         with pytest.raises(IdkPtError):
             pt.SetScene(bad)
-        bad.textures[0] = dict(format=capi.IDKPT_TEX_BC7_SRGB, width=8, height=8, data=np.zeros(64, np.uint8), wrap_s=10497, wrap_t=10497, flags=2)
+        bad.textures[0] = dict(format=capi.IDKPT_TEX_BC7_SRGB, width=8, height=8, data=np.zeros(64, np.uint8), wrap_s=10497, wrap_t=10497, flags=64)      # unknown flag bit
         with pytest.raises(IdkPtError):
             pt.SetScene(bad)
