@@ -253,7 +253,10 @@ IDKPT_API int idkpt_unregister_host_buffer(IdkPtCtx* ctx, void* host_ptr);
  * IDKPT_GATHER_TIMEOUT_MS, default 30 s, if a peer never delivers). idkpt_resize drops the mappings: export / exchange /
  * import again afterwards.
  * idkpt_gather_connect does the same for a host that drives every GPU from ONE process (like the reference engine): pass
- * the contexts in tile order (context r created with TileIndex r, TileCount world); no IPC, peer access is enabled here. */
+ * the contexts in tile order (context r created with TileIndex r, TileCount world); no IPC, peer access is enabled here.
+ * With ONE host thread feeding all contexts only queue work afterwards (idkpt_compute with stats == NULL): a synchronous call
+ * would wait for peers whose work has not been submitted yet (and fail after the time-out). Resizing or destroying one
+ * context invalidates what its peers hold of it: resize all, then connect again. */
 #define IDKPT_GATHER_HANDLE_BYTES 320
 IDKPT_API int idkpt_gather_export(IdkPtCtx* ctx, void* handles_out, uint64_t bytes);
 IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, const void* all_handles, uint64_t bytes);

@@ -49,6 +49,7 @@ inline IdkPtPostSettings DefaultPostSettings() {
 
 struct Tile {
     int StripeHeight = 8, Index = 0, Count = 1;   // multi-GPU screen split: one PathTracer per GPU
+    bool GlobalSlots = false;                     // IDKPT_CREATE_GLOBAL_SLOTS: the N tiles reproduce the untiled image bit for bit
 };
 
 class PathTracer {
@@ -60,7 +61,7 @@ public:
         IdkPtCreateInfo ci = {};
         ci.Device = device; ci.Width = width; ci.Height = height;
         ci.TileStripeHeight = tile.StripeHeight; ci.TileIndex = tile.Index; ci.TileCount = tile.Count;
-        ci.Flags = IDKPT_CREATE_LANES(lanes);
+        ci.Flags = IDKPT_CREATE_LANES(lanes) | (tile.GlobalSlots ? IDKPT_CREATE_GLOBAL_SLOTS : 0u);
         const int rc = idkpt_create(&ci, &ctx_);
         if (rc != IDKPT_OK) {
             const char* msg = idkpt_last_error(nullptr);
@@ -173,6 +174,20 @@ public:
     void ReadRange(IdkPtArrayId which, uint64_t first, uint64_t count, void* out) const { check(idkpt_read_range(ctx_, which, first, count, out), "idkpt_read_range"); }
 
     IdkPtCtx* Handle() const { return ctx_; }
+
+    // One process driving N GPUs (like the engine): tracers in tile order (tracer r created with Tile{.., r, N}). Afterwards every
+    // Compute() also delivers this tile into every tracer's full frame over peer memory (PresentAsync(.., IDKPT_IMAGE_GATHERED)).
+    // With one host thread only queue work (Compute without stats): a synchronous call would wait for peers not yet submitted.
+    static void ConnectPeers(const std::vector<PathTracer*>& tracers) {
+        std::vector<IdkPtCtx*> ctxs;
+        for (PathTracer* t : tracers) ctxs.push_back(t->ctx_);
+        const int rc = idkpt_gather_connect(ctxs.data(), (int32_t)ctxs.size());
+        if (rc != IDKPT_OK) {
+            std::string msg;
+            for (IdkPtCtx* c : ctxs) { const char* m = idkpt_last_error(c); if (m && *m) { msg = m; break; } }
+            throw Error(rc, "idkpt_gather_connect failed: " + msg);
+        }
+    }
 
 private:
     void check(int rc, const char* what) const {

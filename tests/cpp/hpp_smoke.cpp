@@ -25,6 +25,14 @@ int main() {
         idk::Voxelizer vx(16, 16, 16, mn, mx);
         if (vx.LevelCount() != 5) return 1;
         try { vx.Render(); return 1; } catch (const idk::Error& e) { if (e.status() != IDKPT_ERR_NO_SCENE) return 1; }
+        {   // single-process multi-GPU wiring: two tile contexts with global slots connect; a mismatched pair is refused
+            idk::Tile t0, t1;
+            t0.Index = 0; t0.Count = 2; t0.GlobalSlots = true;
+            t1.Index = 1; t1.Count = 2; t1.GlobalSlots = true;
+            idk::PathTracer a(64, 48, idk::DefaultSettings().Gpu, 0, t0, 2), b(64, 48, idk::DefaultSettings().Gpu, 0, t1, 2);
+            idk::PathTracer::ConnectPeers({&a, &b});
+            try { idk::PathTracer::ConnectPeers({&b, &a}); return 1; } catch (const idk::Error& e) { if (e.status() != IDKPT_ERR_INVALID_ARGUMENT) return 1; }
+        }
         std::puts("OK device");
         return 0;
     } catch (const idk::Error& e) {
