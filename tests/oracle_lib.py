@@ -212,16 +212,24 @@ def _vx_declare():
     return L
 
 
-def vx_voxelize(scene, ci, threads=None):
-    """Returns (list of float16 [d,h,w,4] arrays per level, concatenated raw uint16 chain, fragment count)."""
+def vx_voxelize(scene, ci, threads=None, raster_rule=0):
+    """Returns (list of float16 [d,h,w,4] arrays per level, concatenated raw uint16 chain, fragment count).
+    raster_rule: 0 = the product's coverage rule (what the GPU kernels implement), 1 = the GL model (1/256-pixel snapping +
+    top-left fill rule) used only to measure the distance between the two."""
     from idkengine_b200 import vxgi
     L = _vx_declare()
+    L.oracle_vx_set_raster_rule.restype = None
+    L.oracle_vx_set_raster_rule.argtypes = [ctypes.c_int]
+    L.oracle_vx_set_raster_rule(int(raster_rule))
     sizes = vxgi.level_sizes(ci)
     total = sum(w * h * d for w, h, d in sizes)
     raw = np.zeros(total * 4, np.uint16)
     d, keep = capi.scene_desc(scene)
     frags = ctypes.c_uint64()
-    n = L.oracle_vx_voxelize(ctypes.byref(d), ctypes.byref(ci), raw.ctypes.data, total, ctypes.byref(frags), threads or default_threads())
+    try:
+        n = L.oracle_vx_voxelize(ctypes.byref(d), ctypes.byref(ci), raw.ctypes.data, total, ctypes.byref(frags), threads or default_threads())
+    finally:
+        L.oracle_vx_set_raster_rule(0)
     assert n == len(sizes), n
     levels, off = [], 0
     for (w, h, dd) in sizes:
