@@ -98,6 +98,7 @@ struct IdkPtCtx {
     DevBuf counters;               // TraceCounters
     DevBuf countLog;               // per-sample copies of the alive counts (stats only)
     uint32_t epochStart = 0;       // IDKPT_DEBUG_EPOCH_START: first compaction epoch of a fresh lane (wrap-around test hook)
+    uint32_t slotEpochStart = 0;   // IDKPT_DEBUG_SLOT_EPOCH_START: slot-exchange epoch right after the peers are connected (wrap-around test hook)
     bool exportEnabled = false;
 
     // launch configuration
@@ -563,6 +564,7 @@ IDKPT_API int idkpt_create(const IdkPtCreateInfo* ci, IdkPtCtx** out) {
     ctx->globalSlots = (ci->Flags & IDKPT_CREATE_GLOBAL_SLOTS) != 0;
     if (const char* v = getenv("IDKPT_LANES")) ctx->laneCount = std::max(1, std::min(IDK_MAX_LANES, atoi(v)));
     if (const char* v = getenv("IDKPT_DEBUG_EPOCH_START")) ctx->epochStart = (uint32_t)strtoul(v, nullptr, 0) & IDK_EPOCH_MASK;
+    if (const char* v = getenv("IDKPT_DEBUG_SLOT_EPOCH_START")) ctx->slotEpochStart = (uint32_t)strtoul(v, nullptr, 0) & ~1u;   // even: keeps the parity sequence
     if (const char* v = getenv("IDKPT_GATHER_TIMEOUT_MS")) ctx->gatherTimeoutMs = std::max(1.0, atof(v));
     ctx->clockKHz = prop.clockRate;
     compute_tile_rows(ctx);
@@ -1053,7 +1055,11 @@ IDKPT_API int idkpt_compute(IdkPtCtx* ctx, const GpuPerFrameData* frame, const I
                 // per-stripe alive counts of this bounce to every peer, everybody's counts back: global slot = local slot + delta[stripe]
                 SlotExchangeArgs xa;
                 memset(&xa, 0, sizeof(xa));
-                const uint32_t epoch = ++ln.slotEpoch;   // 32 bits: ~20 days at 2,400 exchanges per second and lane
+                // 32-bit epoch (~20 days at 2,400 exchanges per second and lane). Wrap: 0 means "nothing published" and the parity
+                // must keep alternating (0xFFFFFFFF is odd), so the successor of 0xFFFFFFFF is 2. A table word always holds the
+                // epoch of two exchanges ago, so a reused value can never be mistaken for the current one.
+                if (++ln.slotEpoch == 0u) ln.slotEpoch = 2u;
+                const uint32_t epoch = ln.slotEpoch;
                 const size_t laneIdx = (size_t)(&ln - ctx->lanes);
                 for (int p = 0; p < ctx->gatherWorld; p++)
                     xa.peerTable[p] = (unsigned long long*)ctx->peerSlotTable[p] + (laneIdx * 2 + (epoch & 1u)) * (size_t)ctx->nStripes;
@@ -1465,7 +1471,7 @@ IDKPT_API int idkpt_gather_import(IdkPtCtx* ctx, int32_t rank, int32_t world, co
     ctx->gatherRank = rank;
     ctx->gatherEpoch = 0;
     ctx->gatherCurrent = -1;
-    for (int i = 0; i < IDK_MAX_LANES; i++) ctx->lanes[i].slotEpoch = 0;
+    for (int i = 0; i < IDK_MAX_LANES; i++) ctx->lanes[i].slotEpoch = ctx->slotEpochStart;
     return IDKPT_OK;
 }
 
@@ -1511,7 +1517,7 @@ IDKPT_API int idkpt_gather_connect(IdkPtCtx** ctxs, int32_t world) {
         ctx->gatherRank = r;
         ctx->gatherEpoch = 0;
         ctx->gatherCurrent = -1;
-        for (int i = 0; i < IDK_MAX_LANES; i++) ctx->lanes[i].slotEpoch = 0;
+        for (int i = 0; i < IDK_MAX_LANES; i++) ctx->lanes[i].slotEpoch = ctx->slotEpochStart;
     }
     return IDKPT_OK;
 }

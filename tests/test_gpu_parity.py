@@ -463,8 +463,8 @@ def test_multi_gpu_peer_gather():
     assert out.returncode == 0 and "PEER_GATHER_OK" in out.stdout, out.stdout[-1000:] + out.stderr[-2000:]
 
 
-@pytest.mark.parametrize("world", [2, 3])
-def test_global_slots_tiles_equal_one_gpu_image(world):
+@pytest.mark.parametrize("world,epoch_start", [(2, None), (3, None), (2, "0xFFFFFFF8")])
+def test_global_slots_tiles_equal_one_gpu_image(world, epoch_start):
     """SURVEY 8e option (ii), strict multi-GPU parity: `world` tile contexts with IDKPT_CREATE_GLOBAL_SLOTS, wired to each other
     in one process by idkpt_gather_connect (so this runs on a single-GPU box, through the same peer-memory scatter / arrival
     wait / per-bounce slot exchange kernels the multi-process path uses), reproduce the untiled image bit for bit -- in their
@@ -475,6 +475,8 @@ def test_global_slots_tiles_equal_one_gpu_image(world):
     import sys
     repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ, CUDA_DEVICE_MAX_CONNECTIONS="32", IDKPT_GATHER_TIMEOUT_MS="3000")   # fresh process: enough hardware queues for all streams
+    if epoch_start:      # the 32-bit exchange epoch wraps inside the run (successor of 0xFFFFFFFF is 2: parity keeps alternating, 0 stays "unpublished")
+        env["IDKPT_DEBUG_SLOT_EPOCH_START"] = epoch_start
     out = subprocess.run([sys.executable, os.path.join(repo, "scripts", "check_global_slots.py"), "--world", str(world)],
                          capture_output=True, text=True, timeout=300, env=env)
     assert out.returncode == 0, out.stdout[-1500:] + out.stderr[-2500:]
