@@ -5,7 +5,7 @@
  * Replaces (reference paths relative to IDKEngine/):
  *   Source/Render/VXGI/Voxelizer/Voxelizer.cs:109-228   Voxelizer.Render = ClearTextures + Voxelize (+Merge) + Mipmap
  *   Source/Render/VXGI/ConeTracing/ConeTracer.cs:37-50  ConeTracer.Compute
- *   Resource/Shaders/VXGI/Voxelize/{Clear,Voxelize,MergeIntermediates,Mipmap}, VXGI/ConeTraceGI/**, include/TraceCone.glsl
+ *   Resource/Shaders/VXGI/Voxelize/{Clear,Voxelize,MergeIntermediates,Mipmap}, VXGI/ConeTraceGI (all files), include/TraceCone.glsl
  * Call sites in the engine: RasterPipeline.Render (Source/Render/RasterPipeline.cs:306-327,436-439).
  *
  * The reference voxelises with the GL rasteriser (one draw per dominant axis via NV passthrough geometry shader +
