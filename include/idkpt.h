@@ -76,7 +76,8 @@ typedef struct IdkPtCreateInfo {
 /* Material textures. The reference stores 64-bit GL bindless sampler handles in GpuMaterial (GpuMaterial.cs:8-67); here a
  * handle is an index into this table: 0 = the 1x1 white fallback (ModelLoader.cs:1855-1870), k > 0 = Textures[k-1]. Base
  * level only: the path tracer's compute shaders sample lod 0 (Surface.glsl:57-60). Uncompressed RGBA8 as the loader
- * creates for non-KTX images (BaseColor/Emissive sRGB, ModelLoader.cs:938-945); BCn/KTX2 sources are transcoded on the host.
+ * creates for non-KTX images (BaseColor/Emissive sRGB, ModelLoader.cs:938-945), or the BC7 / BC5 / BC4 level-0 block stream of
+ * a KTX2 image as it comes out of the loader's transcoder (decoded on the GPU at upload).
  * Channel use as in Surface.glsl:49-77: BaseColor rgba, MetallicRoughness r = metallic g = roughness, Normal rg,
  * Emissive rgb, Transmission r. */
 typedef enum IdkPtTextureFormat {
